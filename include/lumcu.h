@@ -1,0 +1,146 @@
+/*
+ * lumcu.h -- C-ABI of the B200 radiance stage (liblumcu.so).
+ *
+ * This is the seam a Lum maintainer binds in place of the Vulkan calls of the radiance pass:
+ * every entry point cites the reference code it replaces (paths relative to the reference
+ * tree, platonvin/lum).  POD types and plain pointers only; no C++/CUDA/torch types cross it.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (LUMCU_E_*); lumcu_last_error() gives
+ *     the message of the last failure on the calling thread.  (The reference aborts on error,
+ *     src/macros + lum-al VK_CHECK; the C++ facade turns a non-zero code into abort().)
+ *   - one context = one CUDA device = one host thread at a time (reference: single render
+ *     thread, al.cpp:315-317).  All work is enqueued on the context's stream; calls that
+ *     return data to the host (download_*, last_update_ms) synchronise that stream.
+ *   - host buffers are consumed before the call returns (reference: renderer.cpp:135-138,
+ *     load_stuff.cpp:80,105); the caller never sees device memory except through the
+ *     explicit *_device_ptr getters (interop / tests / NCCL plumbing).
+ *   - there is NO CPU fallback: without a CUDA device lumcu_create fails with LUMCU_E_CUDA.
+ *
+ * Data layouts (kept from Lum)
+ *   world      int16  [z][y][x]      block ids, x fastest        (internal_render.hpp:136-139)
+ *   bricks     uint8  [id][x][y][z]  material ids, z fastest     (internal_types.hpp:46)
+ *   materials  float  [256][6]       r,g,b,a,emmit,rough         (internal_types.hpp:26-30)
+ *   field      uint32 [z][y][x]      A2B10G10R10 unorm           (internal_render.hpp:456)
+ *   requests   int16  [n][4]         x,y,z,0  (reference: i8vec4, internal_render.hpp:410;
+ *                                     widened so worlds larger than 127 blocks are addressable)
+ */
+#ifndef LUMCU_H
+#define LUMCU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUMCU_OK            0
+#define LUMCU_E_ARG        -1   /* bad argument                                  */
+#define LUMCU_E_CUDA       -2   /* CUDA runtime error (incl. "no device")        */
+#define LUMCU_E_STATE      -3   /* call order violated (e.g. update before upload) */
+
+#define LUMCU_DEBUG_PRE_BLEND   1   /* per-workgroup mean radiance before the temporal mix */
+#define LUMCU_DEBUG_RAYS        2   /* per-ray marching-sample count and hit flag          */
+
+typedef struct LumcuCtx LumcuCtx;
+
+/* Resource description; replaces the sizes baked into createImages()
+ * (src/renderer/src/internal_render.cpp:107-209) and the shader constants
+ * (shaders/common/consts.glsl:1, shaders/radiance.comp:27-28,37). */
+typedef struct LumcuDesc {
+    int32_t world_size[3];             /* blocks; reference default 48,48,16                      */
+    int32_t palette_capacity;          /* bricks addressable, 1..4096 (64x64 atlas, internal_types.hpp:16-18) */
+    int32_t rays_per_probe;            /* 16,32,64,128,256; reference 64 (radiance.comp:37)       */
+    float   reactiveness;              /* REACTIVNESS, reference 0.01 (radiance.comp:28)          */
+    int32_t device;                    /* CUDA device ordinal                                     */
+    int64_t max_requests;              /* 0 -> world cells + 4096                                 */
+} LumcuDesc;
+
+const char *lumcu_last_error(void);
+int lumcu_version(void);
+
+/* createImages + setupDescriptors + createPipilines for the radiance pass
+ * (internal_render.cpp:128-135,198-207,236-243,588).  The field starts as all-zero words. */
+int lumcu_create(const LumcuDesc *desc, LumcuCtx **out);
+/* cleanup() of those resources (internal_render.cpp deleteImages / destroy pipes). */
+int lumcu_destroy(LumcuCtx *ctx);
+
+/* end_blockify + the world part of exec_copies: stagingWorld -> world image
+ * (internal_render.cpp:1092-1103,1375-1476).  world_xyz: world_size x*y*z int16. */
+int lumcu_upload_world(LumcuCtx *ctx, const int16_t *world_xyz);
+
+/* updateBlockPalette (load_stuff.cpp:36-86) and the per-block brick copies of exec_copies
+ * (internal_render.cpp:1402-1446): bricks [first_id, first_id+count) in BlockVoxels layout. */
+int lumcu_upload_bricks(LumcuCtx *ctx, int32_t first_id, int32_t count, const uint8_t *voxels);
+
+/* updateMaterialPalette (load_stuff.cpp:89-111): Material[256] as 6 floats each. */
+int lumcu_upload_materials(LumcuCtx *ctx, const float *materials);
+
+/* The staging copy + vkCmdCopyBuffer of the request list (internal_render.cpp:1170-1184).
+ * If a probe appears more than once, which of its workgroups' results is kept is unspecified
+ * (the reference races the same way, internal_render.cpp:1164-1168 keeps duplicate specials). */
+int lumcu_set_requests(LumcuCtx *ctx, const int16_t *xyzw, int64_t n);
+
+/* Device-side restatement of the request-list builder (internal_render.cpp:1142-1169): probes
+ * whose edge-clamped 3x3x3 neighbourhood of the uploaded world sums > 0, in z,y,x order, then the
+ * special requests not already selected, in submission order.  out_count may be NULL. */
+int lumcu_build_requests(LumcuCtx *ctx, const int16_t *special_xyzw, int32_t nspecial, int64_t *out_count);
+int lumcu_request_count(LumcuCtx *ctx, int64_t *out_count);
+int lumcu_download_requests(LumcuCtx *ctx, int16_t *out_xyzw, int64_t cap);
+
+/* Push constants + vkCmdDispatch(N/size) of radiance.comp (internal_render.cpp:1202-1213;
+ * shaders/radiance.comp:361-414): workgroup w in [0, N/size) updates request w*size+shift with
+ * RNG seed time_seed.  Jacobi semantics: every read of the field sees the state before the call. */
+int lumcu_update(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift);
+/* Same, restricted to workgroups [wg_begin, wg_end) of that dispatch (probe sharding across
+ * GPUs: each rank runs its slab of the z-sorted list; seeds keep using the global w). */
+int lumcu_update_range(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift,
+                       int64_t wg_begin, int64_t wg_end);
+/* Workgroup range [wg_begin, wg_end) of the dispatch (size, shift) whose probes have z in
+ * [z_begin, z_end), searched over the leading z-sorted part of the request list (everything the
+ * builder rule produced; for lumcu_set_requests the longest z-monotonic prefix). */
+int lumcu_slab_range(LumcuCtx *ctx, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end,
+                     int64_t *wg_begin, int64_t *wg_end);
+/* lumcu_update restricted to the probes of one z-slab (the unit of multi-GPU sharding, one slab
+ * per rank): the slab's range of the sorted part plus those unsorted tail requests (specials)
+ * whose z falls in the slab.  The union over disjoint slabs equals lumcu_update. */
+int lumcu_update_slab(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift,
+                      int32_t z_begin, int32_t z_end);
+
+/* shift_radiance (internal_render.cpp:1218-1335): field[p] = field[p + d] over the overlap box. */
+int lumcu_shift(LumcuCtx *ctx, int32_t dx, int32_t dy, int32_t dz);
+
+/* Field snapshots (the reference never reads the image back; needed by tests and by any
+ * host-side consumer).  field_xyz: world cells uint32. */
+int lumcu_upload_field(LumcuCtx *ctx, const uint32_t *field_xyz);
+int lumcu_download_field(LumcuCtx *ctx, uint32_t *field_xyz);
+
+/* The 64-entry sphericalFibonacci table the kernel uses (radiance.comp:293-314, evaluated on the
+ * host in f32 at create time).  out: rays_per_probe*3 floats. */
+int lumcu_direction_table(LumcuCtx *ctx, float *out);
+
+/* Instrumentation (parity tests + roofline numerator).  flags = LUMCU_DEBUG_* bits; while
+ * non-zero, lumcu_update runs the instrumented kernel variant and fills the debug buffers. */
+int lumcu_set_debug(LumcuCtx *ctx, int32_t flags);
+/* pre_blend: nwg*3 floats; ray_samples: nwg*R uint32; ray_hits: nwg*R uint8; totals: S,H,N of
+ * the last instrumented update.  Any pointer may be NULL. */
+int lumcu_download_debug(LumcuCtx *ctx, float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
+                         uint64_t totals[3]);
+
+/* vkDeviceWaitIdle for this stage. */
+int lumcu_wait_idle(LumcuCtx *ctx);
+/* GPU time of the last update, the pair of timestamps around vkCmdDispatch
+ * (internal_render.cpp:1205-1207, :2173 timeTakenByRadiance). */
+int lumcu_last_update_ms(LumcuCtx *ctx, float *ms);
+/* Number of kernels this library launched on the context so far. */
+int lumcu_launch_count(LumcuCtx *ctx, uint64_t *count);
+
+/* Interop getters: raw device addresses and the stream (cudaStream_t) as integers. */
+int lumcu_field_device_ptr(LumcuCtx *ctx, uint64_t *ptr);
+int lumcu_world_device_ptr(LumcuCtx *ctx, uint64_t *ptr);
+int lumcu_stream(LumcuCtx *ctx, uint64_t *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUMCU_H */

@@ -1,0 +1,224 @@
+"""lum_b200 -- B200-native radiance-probe update stage for the Lum voxel renderer.
+
+Python here is plumbing only: a ctypes binding of the C-ABI in include/lumcu.h (the product is
+the CUDA library lum_b200/liblumcu.so) used by tests/ and bench.py.  There is no CPU fallback:
+importing works anywhere, but creating a stage needs the built library and a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblumcu.so")
+
+DEBUG_PRE_BLEND = 1
+DEBUG_RAYS = 2
+
+_lib = None
+
+
+class LumcuError(RuntimeError):
+    pass
+
+
+class LumcuDesc(C.Structure):
+    _fields_ = [("world_size", C.c_int32 * 3), ("palette_capacity", C.c_int32),
+                ("rays_per_probe", C.c_int32), ("reactiveness", C.c_float),
+                ("device", C.c_int32), ("max_requests", C.c_int64)]
+
+
+# every symbol include/lumcu.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "lumcu_last_error": (C.c_char_p, []),
+    "lumcu_version": (C.c_int, []),
+    "lumcu_create": (C.c_int, [C.POINTER(LumcuDesc), C.POINTER(_P)]),
+    "lumcu_destroy": (C.c_int, [_P]),
+    "lumcu_upload_world": (C.c_int, [_P, _P]),
+    "lumcu_upload_bricks": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "lumcu_upload_materials": (C.c_int, [_P, _P]),
+    "lumcu_set_requests": (C.c_int, [_P, _P, C.c_int64]),
+    "lumcu_build_requests": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_int64)]),
+    "lumcu_request_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "lumcu_download_requests": (C.c_int, [_P, _P, C.c_int64]),
+    "lumcu_update": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_update_range": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64]),
+    "lumcu_slab_range": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "lumcu_update_slab": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_shift": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_upload_field": (C.c_int, [_P, _P]),
+    "lumcu_download_field": (C.c_int, [_P, _P]),
+    "lumcu_direction_table": (C.c_int, [_P, _P]),
+    "lumcu_set_debug": (C.c_int, [_P, C.c_int32]),
+    "lumcu_download_debug": (C.c_int, [_P, _P, _P, _P, _P]),
+    "lumcu_wait_idle": (C.c_int, [_P]),
+    "lumcu_last_update_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "lumcu_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "lumcu_field_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "lumcu_world_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "lumcu_stream": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+}
+
+
+def load_library():
+    """dlopen liblumcu.so and bind every declared symbol.  Fails loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LumcuError(f"{LIB_PATH} is not built: run `python -m lum_b200.build` "
+                             "(there is no CPU fallback for the radiance stage)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class RadianceStage:
+    """One device context of the radiance stage (LumcuCtx).  Arrays use Lum's layouts:
+    world int16 [wz,wy,wx]; bricks uint8 [n,16,16,16] (x,y,z); materials float32 [256,6];
+    field uint32 [wz,wy,wx]; requests int16 [n,4]."""
+
+    def __init__(self, world_size, palette_capacity, rays_per_probe=64, reactiveness=0.01,
+                 device=0, max_requests=0):
+        self.lib = load_library()
+        self.wx, self.wy, self.wz = (int(v) for v in world_size)
+        self.rays = int(rays_per_probe)
+        self.cells = self.wx * self.wy * self.wz
+        d = LumcuDesc((C.c_int32 * 3)(self.wx, self.wy, self.wz), int(palette_capacity), self.rays,
+                      float(reactiveness), int(device), int(max_requests))
+        self.ctx = _P()
+        self._ck(self.lib.lumcu_create(C.byref(d), C.byref(self.ctx)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LumcuError(f"lumcu error {rc}: {self.lib.lumcu_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.lumcu_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- uploads --------------------------------------------------------------------------
+    def upload_world(self, world):
+        w = np.ascontiguousarray(world, np.int16)
+        assert w.size == self.cells
+        self._ck(self.lib.lumcu_upload_world(self.ctx, _ptr(w)))
+
+    def upload_bricks(self, first_id, bricks):
+        b = np.ascontiguousarray(bricks, np.uint8).reshape(-1, 4096)
+        self._ck(self.lib.lumcu_upload_bricks(self.ctx, int(first_id), b.shape[0], _ptr(b)))
+
+    def upload_materials(self, materials):
+        m = np.ascontiguousarray(materials, np.float32)
+        assert m.size == 256 * 6
+        self._ck(self.lib.lumcu_upload_materials(self.ctx, _ptr(m)))
+
+    def upload_field(self, field):
+        f = np.ascontiguousarray(field, np.uint32)
+        assert f.size == self.cells
+        self._ck(self.lib.lumcu_upload_field(self.ctx, _ptr(f)))
+
+    def set_requests(self, requests):
+        r = np.ascontiguousarray(requests, np.int16).reshape(-1, 4)
+        self._ck(self.lib.lumcu_set_requests(self.ctx, _ptr(r), r.shape[0]))
+
+    def build_requests(self, special=None):
+        sp = None if special is None else np.ascontiguousarray(special, np.int16).reshape(-1, 4)
+        n = C.c_int64()
+        self._ck(self.lib.lumcu_build_requests(self.ctx, _ptr(sp), 0 if sp is None else sp.shape[0], C.byref(n)))
+        return n.value
+
+    # -- the hot path ---------------------------------------------------------------------
+    def update(self, time_seed, size=1, shift=0):
+        self._ck(self.lib.lumcu_update(self.ctx, int(time_seed), int(size), int(shift)))
+
+    def update_range(self, time_seed, size, shift, wg_begin, wg_end):
+        self._ck(self.lib.lumcu_update_range(self.ctx, int(time_seed), int(size), int(shift),
+                                             int(wg_begin), int(wg_end)))
+
+    def update_slab(self, time_seed, size, shift, z_begin, z_end):
+        self._ck(self.lib.lumcu_update_slab(self.ctx, int(time_seed), int(size), int(shift),
+                                            int(z_begin), int(z_end)))
+
+    def slab_range(self, size, shift, z_begin, z_end):
+        b, e = C.c_int64(), C.c_int64()
+        self._ck(self.lib.lumcu_slab_range(self.ctx, int(size), int(shift), int(z_begin), int(z_end),
+                                           C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def shift(self, dx, dy, dz):
+        self._ck(self.lib.lumcu_shift(self.ctx, int(dx), int(dy), int(dz)))
+
+    # -- readbacks ------------------------------------------------------------------------
+    def request_count(self):
+        n = C.c_int64()
+        self._ck(self.lib.lumcu_request_count(self.ctx, C.byref(n)))
+        return n.value
+
+    def download_requests(self):
+        n = self.request_count()
+        out = np.zeros((max(n, 1), 4), np.int16)
+        self._ck(self.lib.lumcu_download_requests(self.ctx, _ptr(out), out.shape[0]))
+        return out[:n]
+
+    def download_field(self, out=None):
+        if out is None:
+            out = np.empty(self.cells, np.uint32)
+        self._ck(self.lib.lumcu_download_field(self.ctx, _ptr(out)))
+        return out
+
+    def direction_table(self):
+        out = np.zeros((self.rays, 3), np.float32)
+        self._ck(self.lib.lumcu_direction_table(self.ctx, _ptr(out)))
+        return out
+
+    def set_debug(self, flags):
+        self._ck(self.lib.lumcu_set_debug(self.ctx, int(flags)))
+
+    def download_debug(self, nwg, pre_blend=True, rays=False):
+        pre = np.zeros((nwg, 3), np.float32) if pre_blend else None
+        rs = np.zeros(nwg * self.rays, np.uint32) if rays else None
+        rh = np.zeros(nwg * self.rays, np.uint8) if rays else None
+        tot = (C.c_uint64 * 3)()
+        self._ck(self.lib.lumcu_download_debug(self.ctx, _ptr(pre), _ptr(rs), _ptr(rh), tot))
+        return dict(pre_blend=pre, ray_samples=rs, ray_hits=rh, totals=(int(tot[0]), int(tot[1]), int(tot[2])))
+
+    def wait_idle(self):
+        self._ck(self.lib.lumcu_wait_idle(self.ctx))
+
+    def last_update_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.lumcu_last_update_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._ck(self.lib.lumcu_launch_count(self.ctx, C.byref(n)))
+        return n.value
+
+    def field_device_ptr(self):
+        p = C.c_uint64()
+        self._ck(self.lib.lumcu_field_device_ptr(self.ctx, C.byref(p)))
+        return p.value
+
+    def stream(self):
+        p = C.c_uint64()
+        self._ck(self.lib.lumcu_stream(self.ctx, C.byref(p)))
+        return p.value

@@ -1,0 +1,575 @@
+// lumcu.cu -- C-ABI of the B200 radiance stage (see include/lumcu.h).
+//
+// Host side of the stage: device mirror of Lum's world / block palette / material palette,
+// the request buffer, the radiance field, and the launch logic that replaces
+// LumInternalRenderer::update_radiance()'s Vulkan half (internal_render.cpp:1170-1213).
+// There is no CPU path: every entry point needs a CUDA device.
+#include "../../include/lumcu.h"
+#include "radiance_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace lumcu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(LUMCU_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Pinned staging ring: the reference's stagingWorld / stagingRadianceUpdates ring<Buffer>
+// (internal_render.cpp:198-207).  Two slots so the host can fill one while the other drains.
+struct Staging {
+    void *host[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    int next = 0;
+    int acquire(size_t bytes, void **out, int *slot) {
+        int s = next;
+        next ^= 1;
+        if (done[s]) CU(cudaEventSynchronize(done[s]));
+        else CU(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+        if (cap[s] < bytes) {
+            if (host[s]) CU(cudaFreeHost(host[s]));
+            host[s] = nullptr; cap[s] = 0;
+            CU(cudaMallocHost(&host[s], bytes));
+            cap[s] = bytes;
+        }
+        *out = host[s];
+        *slot = s;
+        return 0;
+    }
+    void release() {
+        for (int s = 0; s < 2; s++) {
+            if (host[s]) cudaFreeHost(host[s]);
+            if (done[s]) cudaEventDestroy(done[s]);
+            host[s] = nullptr; done[s] = nullptr; cap[s] = 0;
+        }
+    }
+};
+
+}  // namespace
+
+struct LumcuCtx {
+    LumcuDesc desc{};
+    int wx = 0, wy = 0, wz = 0, R = 64;
+    long long cells = 0;
+    long long max_requests = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool timed = false;
+
+    int16_t *d_world = nullptr;
+    uint8_t *d_bricks = nullptr;
+    float *d_materials = nullptr;
+    uint32_t *d_field = nullptr;
+    uint32_t *d_field_tmp = nullptr;       // shift scratch (lazy)
+    short4 *d_requests = nullptr;
+    uint32_t *d_staged = nullptr;
+    float *d_table = nullptr;
+    std::vector<float> h_table;
+    float sun[3] = {0, 0, 0};
+
+    long long nreq = 0;          // current request count
+    long long nsorted = 0;       // leading requests known to be z-sorted
+    bool have_world = false, have_bricks = false, have_materials = false;
+
+    // builder scratch (lazy)
+    uint8_t *d_flags = nullptr;
+    uint32_t *d_block_counts = nullptr;
+    unsigned long long *d_block_offsets = nullptr;
+    unsigned long long *d_total = nullptr;
+    short4 *d_special = nullptr;
+    long long special_cap = 0;
+    long long *d_bounds = nullptr;
+    uint64_t req_version = 1, slab_key_version = 0;
+    int slab_key[4] = {0, 0, 0, 0};
+    long long slab_val[2] = {0, 0};
+
+    // debug
+    int debug_flags = 0;
+    float *d_pre_blend = nullptr;
+    uint32_t *d_ray_samples = nullptr;
+    uint8_t *d_ray_hits = nullptr;
+    unsigned long long *d_totals = nullptr;
+    long long dbg_nwg = 0;       // workgroups of the last instrumented update
+    long long dbg_wg_begin = 0;
+
+    Staging stage_world, stage_req, stage_misc;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int use(LumcuCtx *c) {
+    if (!c) return fail(LUMCU_E_ARG, "null context");
+    CU(cudaSetDevice(c->desc.device));
+    return 0;
+}
+
+void host_direction_table(int n, std::vector<float> &out) {
+    // sphericalFibonacci (radiance.comp:293-314) in f32, one rounding per operation
+    out.resize((size_t)n * 3);
+    const float PI = 3.1415926535897932384626433832795f;
+    const float PHI = sqrtf(5.0f) * 0.5f + 0.5f;
+    for (int k = 0; k < n; k++) {
+        float i = (float)k, fn = (float)n;
+        float ab = i * (PHI - 1.0f);
+        float mf = ab - floorf(ab);
+        float phi = 2.0f * PI * mf;
+        float ct = 1.0f - (2.0f * i + 1.0f) * (1.0f / fn);
+        float q = 1.0f - ct * ct;
+        q = q < 0.0f ? 0.0f : q;
+        q = 1.0f < q ? 1.0f : q;
+        float st = sqrtf(q);
+        out[3 * k + 0] = cosf(phi) * st;
+        out[3 * k + 1] = sinf(phi) * st;
+        out[3 * k + 2] = ct;
+    }
+}
+
+template <bool DEBUG>
+int launch_update_R(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
+    dim3 grid((unsigned)nwg);
+    switch (c->R) {
+        case 16: radiance_update_wg_kernel<16, DEBUG><<<grid, 16, 0, c->stream>>>(sv, a); break;
+        case 32: radiance_update_wg_kernel<32, DEBUG><<<grid, 32, 0, c->stream>>>(sv, a); break;
+        case 64: radiance_update_wg_kernel<64, DEBUG><<<grid, 64, 0, c->stream>>>(sv, a); break;
+        case 128: radiance_update_wg_kernel<128, DEBUG><<<grid, 128, 0, c->stream>>>(sv, a); break;
+        case 256: radiance_update_wg_kernel<256, DEBUG><<<grid, 256, 0, c->stream>>>(sv, a); break;
+        default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ensure_debug(LumcuCtx *c) {
+    if (!c->d_totals) {
+        CU(cudaMalloc(&c->d_totals, 2 * sizeof(unsigned long long)));
+    }
+    if ((c->debug_flags & LUMCU_DEBUG_PRE_BLEND) && !c->d_pre_blend)
+        CU(cudaMalloc(&c->d_pre_blend, (size_t)c->max_requests * 3 * sizeof(float)));
+    if ((c->debug_flags & LUMCU_DEBUG_RAYS) && !c->d_ray_samples) {
+        CU(cudaMalloc(&c->d_ray_samples, (size_t)c->max_requests * c->R * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->d_ray_hits, (size_t)c->max_requests * c->R));
+    }
+    return 0;
+}
+
+int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begin, long long wg_end,
+              int z_begin, int z_end) {
+    if (!c->have_world || !c->have_bricks || !c->have_materials)
+        return fail(LUMCU_E_STATE, "lumcu_update before world/bricks/materials were uploaded");
+    if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
+    if (shift < 0 || shift >= size) return fail(LUMCU_E_ARG, "shift must be in [0,size)");
+    const long long nwg_all = c->nreq / size;
+    if (wg_begin < 0 || wg_end > nwg_all || wg_begin > wg_end)
+        return fail(LUMCU_E_ARG, "workgroup range [%lld,%lld) outside [0,%lld)", wg_begin, wg_end, nwg_all);
+    const long long nwg = wg_end - wg_begin;
+    if (nwg > 0) {
+        SceneView sv{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity};
+        UpdateArgs a{};
+        a.requests = c->d_requests;
+        a.dir_table = c->d_table;
+        a.staged = c->d_staged;
+        a.wg_begin = wg_begin; a.wg_end = wg_end;
+        a.time_seed = time_seed; a.size = size; a.shift = shift;
+        a.z_begin = z_begin; a.z_end = z_end;
+        a.reactiveness = c->desc.reactiveness;
+        a.sun_x = c->sun[0]; a.sun_y = c->sun[1]; a.sun_z = c->sun[2];
+        if (c->debug_flags) {
+            if (int rc = ensure_debug(c)) return rc;
+            a.dbg_pre_blend = (c->debug_flags & LUMCU_DEBUG_PRE_BLEND) ? c->d_pre_blend : nullptr;
+            a.dbg_samples = (c->debug_flags & LUMCU_DEBUG_RAYS) ? c->d_ray_samples : nullptr;
+            a.dbg_hits = (c->debug_flags & LUMCU_DEBUG_RAYS) ? c->d_ray_hits : nullptr;
+            a.dbg_totals = c->d_totals;
+            CU(cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
+            if (int rc = launch_update_R<true>(c, sv, a, nwg)) return rc;
+            c->dbg_nwg = nwg; c->dbg_wg_begin = wg_begin;
+        } else {
+            if (int rc = launch_update_R<false>(c, sv, a, nwg)) return rc;
+        }
+        const int ct = 256;
+        commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
+            c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lumcu_last_error(void) { return g_err.c_str(); }
+int lumcu_version(void) { return 100; }
+
+int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
+    if (!d || !out) return fail(LUMCU_E_ARG, "null argument");
+    *out = nullptr;
+    if (d->world_size[0] < 1 || d->world_size[1] < 1 || d->world_size[2] < 1 ||
+        d->world_size[0] > 32767 || d->world_size[1] > 32767 || d->world_size[2] > 32767)
+        return fail(LUMCU_E_ARG, "world_size out of range");
+    if ((long long)d->world_size[0] * d->world_size[1] * d->world_size[2] > (1ll << 31) - 1)
+        return fail(LUMCU_E_ARG, "world too large (cells must fit in int32)");
+    if (d->palette_capacity < 1 || d->palette_capacity > 4096)
+        return fail(LUMCU_E_ARG, "palette_capacity must be in [1,4096]");
+    const int R = d->rays_per_probe;
+    if (R != 16 && R != 32 && R != 64 && R != 128 && R != 256)
+        return fail(LUMCU_E_ARG, "rays_per_probe must be one of 16,32,64,128,256");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(LUMCU_E_CUDA, "no CUDA device (%s); this stage has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (d->device < 0 || d->device >= ndev) return fail(LUMCU_E_ARG, "device %d out of range (%d devices)", d->device, ndev);
+    LumcuCtx *c = new (std::nothrow) LumcuCtx();
+    if (!c) return fail(LUMCU_E_ARG, "out of host memory");
+    c->desc = *d;
+    c->wx = d->world_size[0]; c->wy = d->world_size[1]; c->wz = d->world_size[2];
+    c->R = R;
+    c->cells = (long long)c->wx * c->wy * c->wz;
+    c->max_requests = d->max_requests > 0 ? d->max_requests : c->cells + 4096;
+    auto bail = [&](int rc) { lumcu_destroy(c); return rc; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(LUMCU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
+    CUB(cudaSetDevice(d->device));
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreate(&c->ev_begin));
+    CUB(cudaEventCreate(&c->ev_end));
+    CUB(cudaMalloc(&c->d_world, (size_t)c->cells * sizeof(int16_t)));
+    CUB(cudaMalloc(&c->d_bricks, (size_t)d->palette_capacity * 4096));
+    CUB(cudaMalloc(&c->d_materials, 256 * 6 * sizeof(float)));
+    CUB(cudaMalloc(&c->d_field, (size_t)c->cells * sizeof(uint32_t)));
+    CUB(cudaMalloc(&c->d_requests, (size_t)c->max_requests * sizeof(short4)));
+    CUB(cudaMalloc(&c->d_staged, (size_t)c->max_requests * sizeof(uint32_t)));
+    CUB(cudaMalloc(&c->d_table, (size_t)R * 3 * sizeof(float)));
+    CUB(cudaMemsetAsync(c->d_world, 0, (size_t)c->cells * sizeof(int16_t), c->stream));
+    CUB(cudaMemsetAsync(c->d_bricks, 0, (size_t)d->palette_capacity * 4096, c->stream));
+    CUB(cudaMemsetAsync(c->d_materials, 0, 256 * 6 * sizeof(float), c->stream));
+    CUB(cudaMemsetAsync(c->d_field, 0, (size_t)c->cells * sizeof(uint32_t), c->stream));   // initial field = zero words
+    host_direction_table(R, c->h_table);
+    CUB(cudaMemcpyAsync(c->d_table, c->h_table.data(), (size_t)R * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    {   // normalize(vec3(0.5,0.5,-0.9)) (radiance.comp:42), f32, x->y->z dot
+        float x = 0.5f, y = 0.5f, z = -0.9f;
+        float l = sqrtf(x * x + y * y + z * z);
+        c->sun[0] = x / l; c->sun[1] = y / l; c->sun[2] = z / l;
+    }
+    CUB(cudaStreamSynchronize(c->stream));
+#undef CUB
+    *out = c;
+    return 0;
+}
+
+int lumcu_destroy(LumcuCtx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->desc.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_field);
+    cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
+    cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
+    cudaFree(c->d_special); cudaFree(c->d_bounds);
+    cudaFree(c->d_pre_blend); cudaFree(c->d_ray_samples); cudaFree(c->d_ray_hits); cudaFree(c->d_totals);
+    c->stage_world.release(); c->stage_req.release(); c->stage_misc.release();
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, size_t bytes) {
+    void *h; int slot;
+    if (int rc = st.acquire(bytes, &h, &slot)) return rc;
+    memcpy(h, src, bytes);
+    CU(cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(st.done[slot], c->stream));
+    return 0;
+}
+
+int lumcu_upload_world(LumcuCtx *c, const int16_t *world) {
+    if (int rc = use(c)) return rc;
+    if (!world) return fail(LUMCU_E_ARG, "null world");
+    if (int rc = staged_upload(c, c->stage_world, c->d_world, world, (size_t)c->cells * sizeof(int16_t))) return rc;
+    c->have_world = true;
+    return 0;
+}
+
+int lumcu_upload_bricks(LumcuCtx *c, int32_t first, int32_t count, const uint8_t *vox) {
+    if (int rc = use(c)) return rc;
+    if (!vox || count < 0 || first < 0 || first + count > c->desc.palette_capacity)
+        return fail(LUMCU_E_ARG, "brick range [%d,%d) outside palette capacity %d", first, first + count, c->desc.palette_capacity);
+    if (count > 0)
+        if (int rc = staged_upload(c, c->stage_misc, c->d_bricks + (size_t)first * 4096, vox, (size_t)count * 4096)) return rc;
+    c->have_bricks = true;
+    return 0;
+}
+
+int lumcu_upload_materials(LumcuCtx *c, const float *m) {
+    if (int rc = use(c)) return rc;
+    if (!m) return fail(LUMCU_E_ARG, "null materials");
+    if (int rc = staged_upload(c, c->stage_misc, c->d_materials, m, 256 * 6 * sizeof(float))) return rc;
+    c->have_materials = true;
+    return 0;
+}
+
+int lumcu_set_requests(LumcuCtx *c, const int16_t *xyzw, int64_t n) {
+    if (int rc = use(c)) return rc;
+    if (n < 0 || n > c->max_requests) return fail(LUMCU_E_ARG, "request count %lld exceeds max_requests %lld", (long long)n, c->max_requests);
+    if (n > 0 && !xyzw) return fail(LUMCU_E_ARG, "null requests");
+    if (n > 0) {
+        if (int rc = staged_upload(c, c->stage_req, c->d_requests, xyzw, (size_t)n * sizeof(short4))) return rc;
+        long long s = 1;
+        while (s < n && xyzw[4 * s + 2] >= xyzw[4 * (s - 1) + 2]) s++;
+        c->nsorted = s;
+    } else {
+        c->nsorted = 0;
+    }
+    c->nreq = n;
+    c->req_version++;
+    return 0;
+}
+
+int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, int64_t *out_count) {
+    if (int rc = use(c)) return rc;
+    if (!c->have_world) return fail(LUMCU_E_STATE, "lumcu_build_requests before lumcu_upload_world");
+    if (nspecial < 0 || (nspecial > 0 && !special)) return fail(LUMCU_E_ARG, "bad special requests");
+    const long long nblocks = (c->cells + BUILD_THREADS - 1) / BUILD_THREADS;
+    if (!c->d_flags) {
+        CU(cudaMalloc(&c->d_flags, (size_t)c->cells));
+        CU(cudaMalloc(&c->d_block_counts, (size_t)nblocks * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->d_block_offsets, (size_t)nblocks * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
+    }
+    build_count_kernel<<<(unsigned)nblocks, BUILD_THREADS, 0, c->stream>>>(c->d_world, c->wx, c->wy, c->wz, c->d_flags, c->d_block_counts);
+    build_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_block_counts, c->d_block_offsets, nblocks, c->d_total);
+    build_scatter_kernel<<<(unsigned)nblocks, BUILD_THREADS, 0, c->stream>>>(c->d_flags, c->d_block_offsets, c->wx, c->wy, c->wz, c->d_requests, c->max_requests);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    unsigned long long nbuilt = 0, total = 0;
+    if (nspecial > 0) {
+        if (c->special_cap < nspecial) {
+            cudaFree(c->d_special); c->d_special = nullptr; c->special_cap = 0;
+            CU(cudaMalloc(&c->d_special, (size_t)nspecial * sizeof(short4)));
+            c->special_cap = nspecial;
+        }
+        if (int rc = staged_upload(c, c->stage_misc, c->d_special, special, (size_t)nspecial * sizeof(short4))) return rc;
+        CU(cudaMemcpyAsync(&nbuilt, c->d_total, sizeof nbuilt, cudaMemcpyDeviceToHost, c->stream));
+        build_specials_kernel<<<1, 1024, 0, c->stream>>>(c->d_flags, c->wx, c->wy, c->wz, c->d_special, nspecial, c->d_requests, c->d_total, c->max_requests);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(&total, c->d_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (nspecial == 0) nbuilt = total;
+    if ((long long)total > c->max_requests)
+        return fail(LUMCU_E_ARG, "request list (%llu) exceeds max_requests %lld", total, c->max_requests);
+    c->nreq = (long long)total;
+    c->req_version++;
+    c->nsorted = (long long)nbuilt;
+    if (out_count) *out_count = (int64_t)total;
+    return 0;
+}
+
+int lumcu_request_count(LumcuCtx *c, int64_t *out) {
+    if (!c || !out) return fail(LUMCU_E_ARG, "null argument");
+    *out = c->nreq;
+    return 0;
+}
+
+int lumcu_download_requests(LumcuCtx *c, int16_t *out, int64_t cap) {
+    if (int rc = use(c)) return rc;
+    if (!out || cap < c->nreq) return fail(LUMCU_E_ARG, "output too small for %lld requests", c->nreq);
+    if (c->nreq > 0) CU(cudaMemcpyAsync(out, c->d_requests, (size_t)c->nreq * sizeof(short4), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lumcu_update(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift) {
+    if (int rc = use(c)) return rc;
+    if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768)) return rc;
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+int lumcu_update_range(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int64_t wg_begin, int64_t wg_end) {
+    if (int rc = use(c)) return rc;
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, wg_begin, wg_end, -32768, 32768)) return rc;
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+static long long sorted_workgroups(const LumcuCtx *c, int size, int shift) {
+    long long nwg_all = c->nreq / size;
+    long long n = c->nsorted > shift ? (c->nsorted - shift + size - 1) / size : 0;
+    return std::min(nwg_all, n);
+}
+
+int lumcu_slab_range(LumcuCtx *c, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end, int64_t *wg_begin, int64_t *wg_end) {
+    if (int rc = use(c)) return rc;
+    if (size < 1 || shift < 0 || shift >= size || !wg_begin || !wg_end || z_begin > z_end)
+        return fail(LUMCU_E_ARG, "bad slab arguments");
+    if (c->slab_key_version == c->req_version && c->slab_key[0] == size && c->slab_key[1] == shift &&
+        c->slab_key[2] == z_begin && c->slab_key[3] == z_end) {
+        *wg_begin = c->slab_val[0]; *wg_end = c->slab_val[1];
+        return 0;
+    }
+    const long long nwg_sorted = sorted_workgroups(c, size, shift);
+    if (!c->d_bounds) CU(cudaMalloc(&c->d_bounds, 2 * sizeof(long long)));
+    long long init[2] = {nwg_sorted, nwg_sorted}, res[2];
+    CU(cudaMemcpyAsync(c->d_bounds, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    if (nwg_sorted > 0) {
+        const int t = 256;
+        slab_bound_kernel<<<(unsigned)((nwg_sorted + t - 1) / t), t, 0, c->stream>>>(c->d_requests, nwg_sorted, size, shift, z_begin, z_end, c->d_bounds);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(res, c->d_bounds, sizeof res, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->slab_key_version = c->req_version;
+    c->slab_key[0] = size; c->slab_key[1] = shift; c->slab_key[2] = z_begin; c->slab_key[3] = z_end;
+    c->slab_val[0] = res[0]; c->slab_val[1] = res[1];
+    *wg_begin = res[0];
+    *wg_end = res[1];
+    return 0;
+}
+
+int lumcu_update_slab(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
+    if (int rc = use(c)) return rc;
+    int64_t b = 0, e = 0;
+    if (int rc = lumcu_slab_range(c, size, shift, z_begin, z_end, &b, &e)) return rc;
+    const long long nwg_all = c->nreq / size, tail = sorted_workgroups(c, size, shift);
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768)) return rc;
+    if (tail < nwg_all)   // unsorted tail (specials): every rank scans it, keeps its slab's probes
+        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end)) return rc;
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+int lumcu_shift(LumcuCtx *c, int32_t dx, int32_t dy, int32_t dz) {
+    if (int rc = use(c)) return rc;
+    if ((dx == 0 && dy == 0 && dz == 0) || abs(dx) >= c->wx || abs(dy) >= c->wy || abs(dz) >= c->wz) return 0;
+    if (!c->d_field_tmp) CU(cudaMalloc(&c->d_field_tmp, (size_t)c->cells * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(c->d_field_tmp, c->d_field, (size_t)c->cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    const int t = 256;
+    shift_kernel<<<(unsigned)((c->cells + t - 1) / t), t, 0, c->stream>>>(c->d_field, c->d_field_tmp, c->wx, c->wy, c->wz, dx, dy, dz);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lumcu_upload_field(LumcuCtx *c, const uint32_t *f) {
+    if (int rc = use(c)) return rc;
+    if (!f) return fail(LUMCU_E_ARG, "null field");
+    return staged_upload(c, c->stage_misc, c->d_field, f, (size_t)c->cells * sizeof(uint32_t));
+}
+
+int lumcu_download_field(LumcuCtx *c, uint32_t *f) {
+    if (int rc = use(c)) return rc;
+    if (!f) return fail(LUMCU_E_ARG, "null field");
+    CU(cudaMemcpyAsync(f, c->d_field, (size_t)c->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lumcu_direction_table(LumcuCtx *c, float *out) {
+    if (!c || !out) return fail(LUMCU_E_ARG, "null argument");
+    memcpy(out, c->h_table.data(), c->h_table.size() * sizeof(float));
+    return 0;
+}
+
+int lumcu_set_debug(LumcuCtx *c, int32_t flags) {
+    if (int rc = use(c)) return rc;
+    c->debug_flags = flags & (LUMCU_DEBUG_PRE_BLEND | LUMCU_DEBUG_RAYS);
+    if (flags & ~(LUMCU_DEBUG_PRE_BLEND | LUMCU_DEBUG_RAYS)) return fail(LUMCU_E_ARG, "unknown debug flags 0x%x", flags);
+    return 0;
+}
+
+int lumcu_download_debug(LumcuCtx *c, float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, uint64_t totals[3]) {
+    if (int rc = use(c)) return rc;
+    if (!c->d_totals) return fail(LUMCU_E_STATE, "no instrumented update has run (lumcu_set_debug first)");
+    const long long n = c->dbg_nwg, b = c->dbg_wg_begin;
+    if (pre_blend) {
+        if (!c->d_pre_blend) return fail(LUMCU_E_STATE, "LUMCU_DEBUG_PRE_BLEND was not enabled");
+        CU(cudaMemcpyAsync(pre_blend, c->d_pre_blend + 3 * b, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (ray_samples || ray_hits) {
+        if (!c->d_ray_samples) return fail(LUMCU_E_STATE, "LUMCU_DEBUG_RAYS was not enabled");
+        if (ray_samples) CU(cudaMemcpyAsync(ray_samples, c->d_ray_samples + b * c->R, (size_t)n * c->R * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (ray_hits) CU(cudaMemcpyAsync(ray_hits, c->d_ray_hits + b * c->R, (size_t)n * c->R, cudaMemcpyDeviceToHost, c->stream));
+    }
+    unsigned long long t[2] = {0, 0};
+    CU(cudaMemcpyAsync(t, c->d_totals, sizeof t, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (totals) { totals[0] = t[0]; totals[1] = t[1]; totals[2] = (uint64_t)n; }
+    return 0;
+}
+
+int lumcu_wait_idle(LumcuCtx *c) {
+    if (int rc = use(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lumcu_last_update_ms(LumcuCtx *c, float *ms) {
+    if (int rc = use(c)) return rc;
+    if (!ms) return fail(LUMCU_E_ARG, "null argument");
+    if (!c->timed) return fail(LUMCU_E_STATE, "no update has run");
+    CU(cudaEventSynchronize(c->ev_end));
+    CU(cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return 0;
+}
+
+int lumcu_launch_count(LumcuCtx *c, uint64_t *count) {
+    if (!c || !count) return fail(LUMCU_E_ARG, "null argument");
+    *count = c->launches;
+    return 0;
+}
+
+int lumcu_field_device_ptr(LumcuCtx *c, uint64_t *p) {
+    if (!c || !p) return fail(LUMCU_E_ARG, "null argument");
+    *p = (uint64_t)(uintptr_t)c->d_field;
+    return 0;
+}
+int lumcu_world_device_ptr(LumcuCtx *c, uint64_t *p) {
+    if (!c || !p) return fail(LUMCU_E_ARG, "null argument");
+    *p = (uint64_t)(uintptr_t)c->d_world;
+    return 0;
+}
+int lumcu_stream(LumcuCtx *c, uint64_t *s) {
+    if (!c || !s) return fail(LUMCU_E_ARG, "null argument");
+    *s = (uint64_t)(uintptr_t)c->stream;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// radiance_device.cuh -- device-side arithmetic of the radiance-probe update.
+//
+// Restates shaders/radiance.comp of the reference (platonvin/lum) for sm_100a.  The sample
+// sequence of CastRay_fast (radiance.comp:183-291) is reproduced exactly -- it is a 0.5-voxel
+// fixed-step sampler with empty-cell skipping and a <=5-step DDA refinement, not a true DDA --
+// so that results are bit-identical to the CPU oracle.  Arithmetic rules (DESIGN.md "Oracle
+// semantics"): binary32, one rounding per written operation (this translation unit is compiled
+// with -fmad=false; '/' and sqrtf are IEEE under nvcc's default -prec-div/-prec-sqrt), GLSL
+// min/max as `y<x?y:x` / `x<y?y:x`, float->int = cvt.rzi (truncate, saturate, NaN->0).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lumcu {
+
+struct SceneView {
+    const int16_t *__restrict__ world;      // [z][y][x] block ids
+    const uint8_t *__restrict__ bricks;     // [id][x][y][z] material ids
+    const float *__restrict__ materials;    // [256][6]
+    const uint32_t *__restrict__ field;     // [z][y][x] packed A2B10G10R10 (read side)
+    int wx, wy, wz;
+    int capacity;                           // bricks addressable
+};
+
+struct f3 { float x, y, z; };
+struct i3 { int x, y, z; };
+
+__device__ __forceinline__ float gmin(float x, float y) { return (y < x) ? y : x; }
+__device__ __forceinline__ float gmax(float x, float y) { return (x < y) ? y : x; }
+__device__ __forceinline__ int f2i(float f) { return __float2int_rz(f); }
+
+// radiance.comp:51-59
+__device__ __forceinline__ f3 hash33(uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t k = 1103515245u;
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        uint32_t a = ((x >> 8) ^ y) * k;
+        uint32_t b = ((y >> 8) ^ z) * k;
+        uint32_t c = ((z >> 8) ^ x) * k;
+        x = a; y = b; z = c;
+    }
+    const float scale = 1.0f / 4294967296.0f;   // 1.0/float(0xffffffffU)
+    return {(float)x * scale, (float)y * scale, (float)z * scale};
+}
+
+// OpSDiv by 16 (truncating) for any sign; OpSMod 16 is `& 15` (radiance.comp:124-125).
+__device__ __forceinline__ int sdiv16(int a) { return (a + ((a >> 31) & 15)) >> 4; }
+
+// GetVoxel (radiance.comp:121-143).  Out-of-range texel fetches return 0.
+__device__ __forceinline__ int get_voxel(const SceneView &s, int ix, int iy, int iz, int &block_id) {
+    int bx = sdiv16(ix), by = sdiv16(iy), bz = sdiv16(iz);
+    int id = 0;
+    if ((unsigned)bx < (unsigned)s.wx && (unsigned)by < (unsigned)s.wy && (unsigned)bz < (unsigned)s.wz)
+        id = __ldg(s.world + (bx + s.wx * (by + s.wy * bz)));
+    int v = 0;
+    if ((unsigned)id < (unsigned)s.capacity)
+        v = __ldg(s.bricks + ((size_t)id * 4096u + (size_t)(((ix & 15) << 8) | ((iy & 15) << 4) | (iz & 15))));
+    block_id = id;
+    return v;
+}
+
+__device__ __forceinline__ f3 unpack10(uint32_t w) {
+    return {(float)(w & 1023u) / 1023.0f, (float)((w >> 10) & 1023u) / 1023.0f,
+            (float)((w >> 20) & 1023u) / 1023.0f};
+}
+__device__ __forceinline__ uint32_t unorm10(float v) {
+    float c = gmin(gmax(v, 0.0f), 1.0f);
+    if (!(c == c)) c = 0.0f;
+    return (uint32_t)__float2int_rn(c * 1023.0f);
+}
+__device__ __forceinline__ uint32_t pack10(float r, float g, float b) {
+    return unorm10(r) | (unorm10(g) << 10) | (unorm10(b) << 20) | (3u << 30);
+}
+
+__device__ __forceinline__ int wrapi(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+__device__ __forceinline__ f3 lerp3(f3 a, f3 b, float w) {
+    return {a.x + w * (b.x - a.x), a.y + w * (b.y - a.y), a.z + w * (b.z - a.z)};
+}
+
+// sample_radiance (radiance.comp:161-166): LINEAR + REPEAT gather at block-space bp.
+__device__ __forceinline__ f3 gather_field(const SceneView &s, f3 bp) {
+    float fx = floorf(bp.x), fy = floorf(bp.y), fz = floorf(bp.z);
+    float wx = bp.x - fx, wy = bp.y - fy, wz = bp.z - fz;
+    int x0 = wrapi(f2i(fx), s.wx), y0 = wrapi(f2i(fy), s.wy), z0 = wrapi(f2i(fz), s.wz);
+    int x1 = x0 + 1 == s.wx ? 0 : x0 + 1;
+    int y1 = y0 + 1 == s.wy ? 0 : y0 + 1;
+    int z1 = z0 + 1 == s.wz ? 0 : z0 + 1;
+    const uint32_t *f = s.field;
+    int r00 = s.wx * (y0 + s.wy * z0), r10 = s.wx * (y1 + s.wy * z0);
+    int r01 = s.wx * (y0 + s.wy * z1), r11 = s.wx * (y1 + s.wy * z1);
+    uint32_t t000 = __ldg(f + r00 + x0), t100 = __ldg(f + r00 + x1);
+    uint32_t t010 = __ldg(f + r10 + x0), t110 = __ldg(f + r10 + x1);
+    uint32_t t001 = __ldg(f + r01 + x0), t101 = __ldg(f + r01 + x1);
+    uint32_t t011 = __ldg(f + r11 + x0), t111 = __ldg(f + r11 + x1);
+    f3 c00 = lerp3(unpack10(t000), unpack10(t100), wx);
+    f3 c10 = lerp3(unpack10(t010), unpack10(t110), wx);
+    f3 c01 = lerp3(unpack10(t001), unpack10(t101), wx);
+    f3 c11 = lerp3(unpack10(t011), unpack10(t111), wx);
+    return lerp3(lerp3(c00, c10, wy), lerp3(c01, c11, wy), wz);
+}
+
+struct RayResult {
+    f3 light;
+    int samples;   // marching samples (coarse + refinement GetVoxel calls)
+    int hit;
+};
+
+// Ray setup (radiance.comp:370-381) + trace_ray (:316-347) + CastRay_fast (:183-291).
+// gid_x = gl_GlobalInvocationID.x, ray = gid_x % R, fib = direction table entry of `ray`.
+__device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px, int py, int pz,
+                                                     uint32_t gid_x, int ray, f3 fib, int time_seed,
+                                                     f3 sun) {
+    uint32_t sx = gid_x + (uint32_t)time_seed, sy = (uint32_t)time_seed, sz = (uint32_t)time_seed;
+    f3 r1 = hash33(sx, sy, sz);
+    f3 r2 = hash33(sx + 1u, sy, sz);
+    f3 j = {fib.x + 0.1f * ((r1.x - 0.5f) * 2.0f), fib.y + 0.1f * ((r1.y - 0.5f) * 2.0f),
+            fib.z + 0.1f * ((r1.z - 0.5f) * 2.0f)};
+    float len = sqrtf(j.x * j.x + j.y * j.y + j.z * j.z);
+    f3 d = {j.x / len, j.y / len, j.z / len};
+    f3 o = {(float)px * 16.0f + 8.0f, (float)py * 16.0f + 8.0f, (float)pz * 16.0f + 8.0f};
+    o.x += d.x * 6.0f; o.y += d.y * 6.0f; o.z += d.z * 6.0f;
+    o.x += (r2.x - 0.5f) * 2.0f; o.y += (r2.y - 0.5f) * 2.0f; o.z += (r2.z - 0.5f) * 2.0f;
+    if (ray & 1) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
+
+    // ---- coarse march (radiance.comp:198-244) ----
+    const f3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    const f3 corner = {d.x > 0.0f ? 16.0f : 0.0f, d.y > 0.0f ? 16.0f : 0.0f, d.z > 0.0f ? 16.0f : 0.0f};
+    const float wsx = (float)s.wx * 16.0f, wsy = (float)s.wy * 16.0f, wsz = (float)s.wz * 16.0f;
+    float t = 0.0f;
+    int voxel = 0, samples = 0;
+    for (;;) {
+        t += 0.5f;
+        f3 p = {o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
+        int ix = f2i(p.x), iy = f2i(p.y), iz = f2i(p.z);
+        int id;
+        voxel = get_voxel(s, ix, iy, iz, id);
+        samples++;
+        if (id == 0) {
+            float bx = (float)(sdiv16(ix) * 16) + corner.x;
+            float by = (float)(sdiv16(iy) * 16) + corner.y;
+            float bz = (float)(sdiv16(iz) * 16) + corner.z;
+            float ex = bx * inv.x + (-p.x * inv.x);
+            float ey = by * inv.y + (-p.y * inv.y);
+            float ez = bz * inv.z + (-p.z * inv.z);
+            t += gmax(gmin(ex, gmin(ey, ez)), 0.01f);
+        }
+        if (voxel != 0) break;
+        if (p.x < 0.0f || p.y < 0.0f || p.z < 0.0f || p.x >= wsx || p.y >= wsy || p.z >= wsz) break;
+        if (t >= 128.0f) break;
+    }
+
+    RayResult res;
+    if (voxel != 0) {
+        // ---- refinement (radiance.comp:246-288) ----
+        float tb = t - 1.5f;
+        f3 h = {o.x + d.x * tb, o.y + d.y * tb, o.z + d.z * tb};
+        int stx = d.x > 0.0f ? 1 : -1, sty = d.y > 0.0f ? 1 : -1, stz = d.z > 0.0f ? 1 : -1;
+        float c1x = (floorf(h.x) - h.x) / d.x, c1y = (floorf(h.y) - h.y) / d.y, c1z = (floorf(h.z) - h.z) / d.z;
+        f3 tMax = {gmax(c1x, c1x + inv.x), gmax(c1y, c1y + inv.y), gmax(c1z, c1z + inv.z)};
+        f3 tDelta = {1.0f / fabsf(d.x), 1.0f / fabsf(d.y), 1.0f / fabsf(d.z)};
+        int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
+        float ax = 0.0f, ay = 0.0f, az = 0.0f;
+        int id;
+        int vid = get_voxel(s, vx, vy, vz, id);
+        samples++;
+        int it = 0;
+        while ((it++ <= 4) && (vid == 0)) {
+            ax = ((tMax.x <= tMax.y) && (tMax.x <= tMax.z)) ? 1.0f : 0.0f;
+            ay = ((tMax.x >= tMax.y) && (tMax.y <= tMax.z)) ? 1.0f : 0.0f;
+            az = ((tMax.z <= tMax.x) && (tMax.z <= tMax.y)) ? 1.0f : 0.0f;
+            vx += stx * (int)ax; vy += sty * (int)ay; vz += stz * (int)az;
+            tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
+            vid = get_voxel(s, vx, vy, vz, id);
+            samples++;
+        }
+        f3 n = {-((float)stx * ax), -((float)sty * ay), -((float)stz * az)};
+        float tf = (tMax.x - tDelta.x) * ax + (tMax.y - tDelta.y) * ay + (tMax.z - tDelta.z) * az;
+        const float *m = s.materials + 6 * (vid & 255);
+        float mr = __ldg(m), mg = __ldg(m + 1), mb = __ldg(m + 2), me = __ldg(m + 4);
+        // ---- shade hit (radiance.comp:331-333,161-166) ----
+        f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
+        f3 bp = {(x.x + n.x * 16.0f) / 16.0f, (x.y + n.y * 16.0f) / 16.0f, (x.z + n.z * 16.0f) / 16.0f};
+        f3 g = gather_field(s, bp);
+        res.light = {0.0f + (1.0f * g.x * mr + mr * me), 0.0f + (1.0f * g.y * mg + mg * me),
+                     0.0f + (1.0f * g.z * mb + mb * me)};
+        res.hit = 1;
+    } else {
+        // ---- sky (radiance.comp:334-344) ----
+        float glp = -(d.x * sun.x + d.y * sun.y + d.z * sun.z);
+        f3 l = {0.0f, 0.0f, 0.0f};
+        if (glp > 0.95f) {
+            l.x += 1.0f * glp * (0.9f * 3.0f);
+            l.y += 1.0f * glp * (0.9f * 3.0f);
+            l.z += 1.0f * glp * (0.6f * 3.0f);
+        }
+        l.x += 1.0f * (0.53f * 0.1f);
+        l.y += 1.0f * (0.81f * 0.1f);
+        l.z += 1.0f * (0.92f * 0.1f);
+        res.light = l;
+        res.hit = 0;
+    }
+    res.samples = samples;
+    return res;
+}
+
+}  // namespace lumcu

@@ -1,0 +1,182 @@
+"""ctypes wrapper around the CPU oracle (oracle/lum_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/lum_oracle.h).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+module.  The product package (lum_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblum_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle (and oracle/_ref when the reference tree is present)."""
+    src = os.path.join(_HERE, "lum_oracle.c")
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("lum_oracle.c", "lum_oracle.h", "Makefile"))
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    assert os.path.exists(src)
+    return _LIB_PATH
+
+
+class _Scene(C.Structure):
+    _fields_ = [("wx", C.c_int), ("wy", C.c_int), ("wz", C.c_int),
+                ("palette_capacity", C.c_int), ("rays_per_probe", C.c_int),
+                ("reactiveness", C.c_float),
+                ("world", C.c_void_p), ("bricks", C.c_void_p), ("materials", C.c_void_p)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("light", C.c_float * 3), ("origin", C.c_float * 3), ("dir", C.c_float * 3),
+                ("fraction", C.c_float), ("normal", C.c_float * 3), ("hit", C.c_int32),
+                ("coarse_samples", C.c_int32), ("refine_samples", C.c_int32), ("voxel", C.c_int32)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.lum_oracle_build_requests.restype = C.c_int64
+        _lib.lum_oracle_update.restype = C.c_int
+        _lib.lum_oracle_pack_rgb10a2.restype = C.c_uint32
+        _lib.lum_oracle_max_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Scene:
+    """world int16 [wz,wy,wx]; bricks uint8 [P,16,16,16] (x,y,z); materials float32 [256,6]."""
+
+    def __init__(self, world, bricks, materials, rays_per_probe=64, reactiveness=0.01):
+        self.world = np.ascontiguousarray(world, dtype=np.int16)
+        self.bricks = np.ascontiguousarray(bricks, dtype=np.uint8)
+        self.materials = np.ascontiguousarray(materials, dtype=np.float32)
+        assert self.world.ndim == 3 and self.bricks.shape[1:] == (16, 16, 16)
+        assert self.materials.shape == (256, 6)
+        self.wz, self.wy, self.wx = self.world.shape
+        self.rays = int(rays_per_probe)
+        self.c = _Scene(self.wx, self.wy, self.wz, self.bricks.shape[0], self.rays,
+                        np.float32(reactiveness), _p(self.world), _p(self.bricks), _p(self.materials))
+
+    @property
+    def cells(self):
+        return self.wx * self.wy * self.wz
+
+
+def hash33(x, y, z):
+    i = (C.c_uint32 * 3)(x & 0xFFFFFFFF, y & 0xFFFFFFFF, z & 0xFFFFFFFF)
+    u = (C.c_uint32 * 3)()
+    f = (C.c_float * 3)()
+    lib().lum_oracle_hash33(i, u, f)
+    return tuple(u), tuple(f)
+
+
+def direction_table(n=64):
+    out = np.zeros((n, 3), np.float32)
+    lib().lum_oracle_direction_table(C.c_int(n), _p(out))
+    return out
+
+
+def sun_dir():
+    out = np.zeros(3, np.float32)
+    lib().lum_oracle_sun_dir(_p(out))
+    return out
+
+
+def pack(rgb):
+    a = (C.c_float * 3)(*[float(v) for v in rgb])
+    return int(lib().lum_oracle_pack_rgb10a2(a))
+
+
+def unpack(word):
+    out = (C.c_float * 3)()
+    lib().lum_oracle_unpack_rgb10a2(C.c_uint32(int(word)), out)
+    return np.array(list(out), np.float32)
+
+
+def get_voxel(scene: Scene, x, y, z):
+    out = (C.c_int * 2)()
+    lib().lum_oracle_get_voxel(C.byref(scene.c), C.c_int(x), C.c_int(y), C.c_int(z), out)
+    return out[0], out[1]
+
+
+def gather(scene: Scene, field, bp):
+    field = np.ascontiguousarray(field, np.uint32)
+    a = (C.c_float * 3)(*[float(v) for v in bp])
+    out = (C.c_float * 3)()
+    lib().lum_oracle_gather(C.byref(scene.c), _p(field), a, out)
+    return np.array(list(out), np.float32)
+
+
+def build_requests(world, special=None):
+    world = np.ascontiguousarray(world, np.int16)
+    wz, wy, wx = world.shape
+    sp = None if special is None else np.ascontiguousarray(special, np.int16).reshape(-1, 4)
+    nsp = 0 if sp is None else sp.shape[0]
+    cap = world.size + nsp
+    out = np.zeros((cap, 4), np.int16)
+    n = lib().lum_oracle_build_requests(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(world), _p(sp),
+                                        C.c_int(nsp), _p(out), C.c_int64(cap))
+    return out[:n].copy()
+
+
+def trace(scene: Scene, field, probe, gid_x, ray_index, time_seed, table=None):
+    field = np.ascontiguousarray(field, np.uint32)
+    if table is None:
+        table = direction_table(scene.rays)
+    pr = (C.c_int16 * 3)(*[int(v) for v in probe[:3]])
+    r = Ray()
+    lib().lum_oracle_trace(C.byref(scene.c), _p(field), _p(table), pr, C.c_uint32(gid_x),
+                           C.c_int(ray_index), C.c_int(time_seed), C.byref(r))
+    return r
+
+
+def update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, nthreads=0,
+           want_rays=False):
+    """Returns dict(field, pre_blend, totals=(S,H,N), threads[, ray_samples, ray_hits])."""
+    field_old = np.ascontiguousarray(field_old, np.uint32).reshape(-1)
+    assert field_old.size == scene.cells
+    req = np.ascontiguousarray(requests, np.int16).reshape(-1, 4)
+    nreq = req.shape[0]
+    nwg = nreq // size if size > 0 else 0
+    field_new = np.empty_like(field_old)
+    pre = np.zeros((nwg, 3), np.float32)
+    rs = np.zeros(nwg * scene.rays, np.uint32) if want_rays else None
+    rh = np.zeros(nwg * scene.rays, np.uint8) if want_rays else None
+    tot = (C.c_uint64 * 3)()
+    used = lib().lum_oracle_update(C.byref(scene.c), _p(field_old), _p(field_new), _p(req),
+                                   C.c_int64(nreq), C.c_int(time_seed), C.c_int(size), C.c_int(shift),
+                                   _p(pre), _p(rs), _p(rh), tot, C.c_int(nthreads))
+    res = dict(field=field_new, pre_blend=pre, totals=(int(tot[0]), int(tot[1]), int(tot[2])),
+               threads=used)
+    if want_rays:
+        res["ray_samples"] = rs
+        res["ray_hits"] = rh
+    return res
+
+
+def shift_field(field, dims, dx, dy, dz):
+    wx, wy, wz = dims
+    field = np.ascontiguousarray(field, np.uint32).reshape(-1)
+    out = np.empty_like(field)
+    lib().lum_oracle_shift_field(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(field), _p(out),
+                                 C.c_int(dx), C.c_int(dy), C.c_int(dz))
+    return out
+
+
+def max_threads():
+    return int(lib().lum_oracle_max_threads())

@@ -1,0 +1,106 @@
+/*
+ * lum_oracle.h -- CPU restatement (ORACLE) of Lum's radiance-probe update path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may build, load or call it, and there only as the checker / CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (platonvin/lum) has no tests, golden vectors or
+ * fixtures for this path, and its implementation (GLSL shaders/radiance.comp on
+ * Vulkan) cannot be executed in the build container or on the GPU box (no
+ * Vulkan loader / ICD / lavapipe, no SPIR-V executor).  This oracle is therefore
+ * a line-by-line restatement of the shader text with the implementation-defined
+ * points pinned by decree (see DESIGN.md "Oracle semantics"); it is validated
+ * against known-answer values derived by hand from the shader text only.
+ *
+ * All file:line citations are relative to the reference tree (/root/reference).
+ */
+#ifndef LUM_ORACLE_H
+#define LUM_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Scene inputs in Lum's own layouts. */
+typedef struct {
+    int wx, wy, wz;          /* world size in blocks (shaders/common/consts.glsl:1)        */
+    int palette_capacity;    /* bricks addressable (<= 4096 = 64x64 atlas)                  */
+    int rays_per_probe;      /* RAYS_PER_PROBE (radiance.comp:37); reference = 64           */
+    float reactiveness;      /* REACTIVNESS (radiance.comp:28) = 0.01                       */
+    const int16_t *world;    /* [z][y][x] block ids, x fastest (internal_render.hpp:136)   */
+    const uint8_t *bricks;   /* [id][x][y][z] material ids, z fastest (internal_types:46)  */
+    const float   *materials;/* [256][6] r,g,b,a,emmit,rough (internal_types.hpp:26-30)    */
+} LumOracleScene;
+
+/* Per-ray trace record (debug / roofline numerator). */
+typedef struct {
+    float light[3];      /* trace_ray result (radiance.comp:316-347)              */
+    float origin[3];
+    float dir[3];
+    float fraction;      /* final fraction (refined on hit, coarse on miss)       */
+    float normal[3];
+    int32_t hit;         /* 1 = CastRay_fast returned true                        */
+    int32_t coarse_samples; /* iterations of the loop at radiance.comp:205-244    */
+    int32_t refine_samples; /* GetVoxel calls at radiance.comp:267,280            */
+    int32_t voxel;       /* material id used by GetMat on hit                     */
+} LumOracleRay;
+
+/* radiance.comp:51-59 (integer part) and :58 (float scale). */
+void lum_oracle_hash33(const uint32_t in[3], uint32_t out_u[3], float out_f[3]);
+
+/* radiance.comp:293-314, evaluated in f32 on the host; out = [n][3]. */
+void lum_oracle_direction_table(int n, float *out);
+
+/* normalize(vec3(0.5,0.5,-0.9)), radiance.comp:42. */
+void lum_oracle_sun_dir(float out[3]);
+
+/* A2B10G10R10 unorm pack/unpack (internal_render.hpp:456; Vulkan unorm rules). */
+uint32_t lum_oracle_pack_rgb10a2(const float rgb[3]);
+void lum_oracle_unpack_rgb10a2(uint32_t word, float rgb[3]);
+
+/* GetVoxel (radiance.comp:121-143): out[0]=voxel, out[1]=block id at integer voxel position. */
+void lum_oracle_get_voxel(const LumOracleScene *s, int x, int y, int z, int out[2]);
+
+/* sample_radiance gather (radiance.comp:161-166 + sampler setup.cpp:75-81) at block-space bp. */
+void lum_oracle_gather(const LumOracleScene *s, const uint32_t *field, const float bp[3], float rgb[3]);
+
+/* update_radiance request list (internal_render.cpp:1142-1169).
+ * out: int16 x,y,z,w per request; returns the count (may exceed cap: nothing is written past cap). */
+int64_t lum_oracle_build_requests(int wx, int wy, int wz, const int16_t *world,
+                                  const int16_t *special_xyzw, int nspecial,
+                                  int16_t *out_xyzw, int64_t cap);
+
+/* One ray of one workgroup: ray setup (radiance.comp:370-381) + trace_ray (:316-347). */
+void lum_oracle_trace(const LumOracleScene *s, const uint32_t *field,
+                      const float *dir_table, const int16_t probe[3],
+                      uint32_t global_invocation_x, int ray_index, int time_seed,
+                      LumOracleRay *out);
+
+/* Full dispatch: workgroups w in [0, nreq/size) process request w*size+shift
+ * (radiance.comp:361-414, internal_render.cpp:1202-1206).
+ * field_old is read (gather + old texel), field_new receives a copy of field_old
+ * with the processed probes overwritten (Jacobi semantics, decree 1).
+ * Optional outputs (may be NULL): pre_blend [nwg][3] mean radiance before the
+ * temporal mix; ray_samples [nwg*R] marching samples per ray; ray_hits [nwg*R].
+ * totals[0]=S (samples), totals[1]=H (hit rays), totals[2]=N (probes).
+ * nthreads <= 0 -> omp_get_max_threads().  Returns the thread count used. */
+int lum_oracle_update(const LumOracleScene *s, const uint32_t *field_old, uint32_t *field_new,
+                      const int16_t *requests_xyzw, int64_t nreq,
+                      int time_seed, int size, int shift,
+                      float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
+                      uint64_t totals[3], int nthreads);
+
+/* shift_radiance (internal_render.cpp:1218-1335): out[p] = in[p + shift] where p + shift is
+ * inside the world, else unchanged in[p] (the reference copies only the overlapping box via a
+ * temporary image).  |shift| >= world size on any axis is a no-op (the reference tests x only,
+ * :1230-1235, and is undefined for y/z; pinned by decree). */
+void lum_oracle_shift_field(int wx, int wy, int wz, const uint32_t *in, uint32_t *out,
+                            int dx, int dy, int dz);
+
+int lum_oracle_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,260 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (include/lumcu.h), against the CPU
+oracle on the same inputs.  Bar: per-probe pre-blend mean radiance and the
+packed field are BIT-EXACT (integer/byte work and f32 with one rounding per operation on both
+sides); the stated north_star tolerance 1e-5*max(1,|x|) is therefore met with margin 0."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_stage, oracle_scene
+from lum_b200 import DEBUG_PRE_BLEND, DEBUG_RAYS, scenes
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_demo_golden.npz")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_update_equal(st, O, sc, f0, req, seed, size=1, shift=0, rays=True):
+    st.upload_field(f0)
+    st.set_requests(req)
+    st.set_debug(DEBUG_PRE_BLEND | (DEBUG_RAYS if rays else 0))
+    st.update(seed, size, shift)
+    nwg = len(req) // size
+    dbg = st.download_debug(nwg, rays=rays)
+    got = st.download_field()
+    ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=rays)
+    if rays:
+        assert np.array_equal(dbg["ray_samples"], ref["ray_samples"])
+        assert np.array_equal(dbg["ray_hits"], ref["ray_hits"])
+    assert dbg["totals"] == ref["totals"]
+    # -0.0 == +0.0 is allowed; everything else must match bit for bit
+    assert np.array_equal(dbg["pre_blend"], ref["pre_blend"])
+    nz = ref["pre_blend"] != 0
+    assert np.array_equal(bits(dbg["pre_blend"])[nz], bits(ref["pre_blend"])[nz])
+    assert np.array_equal(got, ref["field"])
+    # the non-instrumented kernel gives the same field
+    st.upload_field(f0)
+    st.set_debug(0)
+    st.update(seed, size, shift)
+    assert np.array_equal(st.download_field(), ref["field"])
+    return ref
+
+
+def test_direction_table_matches_oracle(oracle_mod, demo):
+    st = make_stage(demo)
+    assert np.array_equal(bits(st.direction_table()), bits(oracle_mod.direction_table(64)))
+
+
+def test_demo_single_update_config1(oracle_mod, demo):
+    """BASELINE config 1/2: demo world, all 2,689 probes x 64 rays, time_seed 1, zero field."""
+    O = oracle_mod
+    st = make_stage(demo)
+    sc = oracle_scene(O, demo)
+    req = O.build_requests(demo["world"])
+    ref = assert_update_equal(st, O, sc, np.zeros(sc.cells, np.uint32), req, 1)
+    assert ref["totals"][2] == 2689
+
+
+def test_demo_golden_vectors(demo):
+    """Committed golden vectors (no oracle code involved at run time)."""
+    g = np.load(GOLD)
+    st = make_stage(demo)
+    n = st.build_requests()
+    assert n == 2689
+    st.set_debug(DEBUG_PRE_BLEND)
+    for frame in range(int(g["frames"])):
+        st.update(1 + frame)
+        d = st.download_debug(n)
+        assert d["totals"] == tuple(int(v) for v in g["totals"][frame])
+        assert np.array_equal(d["pre_blend"][g["probe_idx"]], g["pre_blend"][frame])
+    assert np.array_equal(st.download_field(), g["field"])
+
+
+@pytest.mark.parametrize("seed", [0, 2, 77, 2 ** 31 - 1, -5])
+def test_demo_seeds_and_random_field(oracle_mod, demo, seed):
+    O = oracle_mod
+    st = make_stage(demo)
+    sc = oracle_scene(O, demo)
+    rng = np.random.default_rng(seed & 0xFFFF)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    req = O.build_requests(demo["world"])
+    assert_update_equal(st, O, sc, f0, req, seed)
+
+
+def test_demo_warm_multiframe(oracle_mod, demo):
+    """config 3 shape (static part): 16 accumulating frames, field fed back each frame."""
+    O = oracle_mod
+    st = make_stage(demo)
+    sc = oracle_scene(O, demo)
+    req = O.build_requests(demo["world"])
+    st.set_requests(req)
+    f = np.zeros(sc.cells, np.uint32)
+    for frame in range(16):
+        st.update(frame)
+        f = O.update(sc, f, req, frame)["field"]
+    assert np.array_equal(st.download_field(), f)
+
+
+@pytest.mark.parametrize("size,shift", [(2, 0), (2, 1), (3, 2), (10, 7)])
+def test_magic_size_dispatch(oracle_mod, demo, size, shift):
+    """magicSize sub-sampling (internal_render.cpp:1190-1206): N/size workgroups, request w*size+shift."""
+    O = oracle_mod
+    st = make_stage(demo)
+    sc = oracle_scene(O, demo)
+    req = O.build_requests(demo["world"])
+    rng = np.random.default_rng(size * 16 + shift)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    assert_update_equal(st, O, sc, f0, req, 9, size=size, shift=shift)
+
+
+def test_specials_and_request_builder(oracle_mod, demo):
+    O = oracle_mod
+    st = make_stage(demo)
+    sp = np.array([(x, y, z, 0) for x in range(5, 12) for y in range(6, 16) for z in (2, 1)], np.int16)
+    n = st.build_requests(sp)
+    ref = O.build_requests(demo["world"], sp)
+    assert n == len(ref) == 2689 + 66
+    assert np.array_equal(st.download_requests(), ref)
+    assert st.build_requests() == 2689
+    assert np.array_equal(st.download_requests(), ref[:2689])
+
+
+@pytest.mark.parametrize("rays", [16, 32, 64, 128, 256])
+def test_synthetic_small_all_ray_counts(oracle_mod, small_synth, rays):
+    O = oracle_mod
+    st = make_stage(small_synth, rays=rays)
+    sc = oracle_scene(O, small_synth, rays=rays)
+    assert np.array_equal(bits(st.direction_table()), bits(O.direction_table(rays)))
+    req = O.build_requests(small_synth["world"])
+    rng = np.random.default_rng(rays)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    assert_update_equal(st, O, sc, f0, req, 4)
+
+
+def test_synthetic_builder_matches_oracle(oracle_mod):
+    sc = scenes.synthetic_scene(67, 33, 9, palette=16, seed=99, p_cell=0.02)
+    st = make_stage(sc)
+    n = st.build_requests()
+    ref = oracle_mod.build_requests(sc["world"])
+    assert n == len(ref)
+    assert np.array_equal(st.download_requests(), ref)
+
+
+def test_edge_cases(oracle_mod, demo):
+    O = oracle_mod
+    sc = oracle_scene(O, demo)
+    st = make_stage(demo)
+    f0 = np.full(sc.cells, 0xFFFFFFFF, np.uint32)
+    # empty request list: field untouched
+    st.upload_field(f0)
+    st.set_requests(np.zeros((0, 4), np.int16))
+    st.update(1)
+    assert np.array_equal(st.download_field(), f0)
+    # probes on every world corner / face (rays leave through low and high faces, REPEAT gather wraps)
+    req = np.array([(x, y, z, 0) for x in (0, 47) for y in (0, 47) for z in (0, 15)] +
+                   [(0, 20, 15, 0), (47, 20, 8, 0), (20, 0, 15, 0), (20, 47, 15, 0)], np.int16)
+    assert_update_equal(st, O, sc, f0, req, 6)
+    # a probe listed alone runs as workgroup 0 whatever its position
+    assert_update_equal(st, O, sc, f0, req[5:6], 6)
+
+
+def test_empty_world_all_sky(oracle_mod):
+    O = oracle_mod
+    scn = dict(world=np.zeros((4, 6, 5), np.int16), bricks=np.zeros((2, 16, 16, 16), np.uint8),
+               materials=np.zeros((256, 6), np.float32))
+    st = make_stage(scn)
+    sc = oracle_scene(O, scn)
+    assert st.build_requests() == 0
+    req = np.array([(x, y, z, 0) for z in range(4) for y in range(6) for x in range(5)], np.int16)
+    ref = assert_update_equal(st, O, sc, np.zeros(sc.cells, np.uint32), req, 1)
+    assert ref["totals"][1] == 0            # no hits: every ray is sky
+
+
+def test_solid_world_and_saturation(oracle_mod):
+    """Every voxel solid and strongly emissive: immediate hits, texels saturate at 1023."""
+    O = oracle_mod
+    mats = np.zeros((256, 6), np.float32); mats[:, :3] = 1.0; mats[:, 4] = 18.0
+    scn = dict(world=np.ones((3, 4, 5), np.int16), bricks=np.full((2, 16, 16, 16), 7, np.uint8), materials=mats)
+    st = make_stage(scn, reactiveness=1.0)
+    sc = oracle_scene(O, scn, reactiveness=1.0)
+    req = O.build_requests(scn["world"])
+    assert len(req) == 60
+    ref = assert_update_equal(st, O, sc, np.zeros(sc.cells, np.uint32), req, 1)
+    assert np.all(ref["field"] == 0xFFFFFFFF)
+
+
+def test_ranges_and_slabs_compose(oracle_mod, demo):
+    """Probe sharding: disjoint workgroup ranges / z-slabs reproduce the full update exactly."""
+    O = oracle_mod
+    sc = oracle_scene(O, demo)
+    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16)   # unsorted tail
+    req = O.build_requests(demo["world"], sp)
+    rng = np.random.default_rng(21)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 12)["field"]
+    st = make_stage(demo)
+    st.set_requests(req)
+    # (a) workgroup ranges on ONE field are NOT Jacobi across calls, so compose on copies
+    n = len(req)
+    cuts = [0, 500, 501, 1700, n]
+    out = f0.copy()
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        st.upload_field(f0)
+        st.update_range(12, 1, 0, b, e)
+        got = st.download_field()
+        ch = got != f0
+        out[ch] = got[ch]
+    assert np.array_equal(out, ref)
+    # (b) z-slabs: each "rank" owns a contiguous z range of the field
+    out = np.empty_like(f0).reshape(16, 48, 48)
+    for r in range(4):
+        st.upload_field(f0)
+        st.update_slab(12, 1, 0, 4 * r, 4 * r + 4)
+        out[4 * r:4 * r + 4] = st.download_field().reshape(16, 48, 48)[4 * r:4 * r + 4]
+    assert np.array_equal(out.reshape(-1), ref)
+    zs = req[:, 2]
+    prefix = n if np.all(np.diff(zs) >= 0) else int(np.argmax(np.diff(zs) < 0)) + 1
+    assert st.slab_range(1, 0, 0, 16) == (0, prefix)
+    assert st.slab_range(1, 0, 4, 8) == (int(np.searchsorted(zs[:prefix], 4)), int(np.searchsorted(zs[:prefix], 8)))
+
+
+def test_shift_matches_oracle(oracle_mod, demo):
+    O = oracle_mod
+    st = make_stage(demo)
+    rng = np.random.default_rng(2)
+    f0 = rng.integers(0, 2 ** 32, 48 * 48 * 16, dtype=np.uint64).astype(np.uint32)
+    for d in [(1, 0, 0), (-3, 2, 1), (0, 0, -15), (47, -47, 0), (48, 0, 0), (0, 0, 0)]:
+        st.upload_field(f0)
+        st.shift(*d)
+        assert np.array_equal(st.download_field(), O.shift_field(f0, (48, 48, 16), *d)), d
+
+
+def test_round_trip_properties_full_size():
+    """Size-independent properties at BASELINE config-4 size (256x256x64, no oracle involved):
+    determinism (same inputs -> same field), every requested texel gets alpha=3, untouched
+    texels keep their words, slabs compose to the full update."""
+    scn = scenes.synthetic_scene(256, 256, 64)
+    st = make_stage(scn)
+    n = st.build_requests()
+    assert n > 4_000_000
+    st.update(1)
+    f1 = st.download_field()
+    st.upload_field(np.zeros(st.cells, np.uint32))
+    st.update(1)
+    assert np.array_equal(st.download_field(), f1)
+    req = st.download_requests()
+    lin = req[:, 0].astype(np.int64) + 256 * (req[:, 1].astype(np.int64) + 256 * req[:, 2].astype(np.int64))
+    assert np.all(f1[lin] >> 30 == 3)
+    mask = np.ones(st.cells, bool); mask[lin] = False
+    assert np.all(f1[mask] == 0)
+    out = np.empty_like(f1).reshape(64, 256, 256)
+    for r in range(2):
+        st.upload_field(np.zeros(st.cells, np.uint32))
+        st.update_slab(1, 1, 0, 32 * r, 32 * r + 32)
+        out[32 * r:32 * r + 32] = st.download_field().reshape(64, 256, 256)[32 * r:32 * r + 32]
+    assert np.array_equal(out.reshape(-1), f1)
