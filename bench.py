@@ -1,0 +1,403 @@
+#!/usr/bin/env python3
+"""bench.py -- radiance-probe rays/s and ms per full radiance-field update (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
+
+A step = one full radiance-field update: every probe selected by Lum's request rule x 64 rays.
+
+Workloads (config.workload):
+  synthetic-256x256x64  BASELINE.json configs[3] (SURVEY.md 8d "C4"): the configuration the metric
+                        is quoted on at 1/2/4/8 GPUs; fits one GPU, so it is the workload at every N
+                        (strong scaling: total work fixed, probes sharded by z-slab, all-gather of
+                        the field each step).  DEFAULT.
+  demo                  BASELINE.json configs[1]: Lum's demo world, full recompute (2,689 probes).
+                        Also measured at N=1 in the default run and reported under "demo".
+
+Timed regions (CUDA events on the stage's stream, L2 flushed between timed steps, max over ranks):
+  value  inputs resident in HBM: update kernel(s) + commit (+ NCCL all-gather when N > 1)
+  e2e    through the C-ABI with HOST buffers: world upload (pinned staging) + device request-list
+         build + update (+ all-gather) + field download
+The oracle (oracle/) is used here only for the cpu_baseline leg and --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "radiance_probe_rays_per_sec"
+UNIT = "rays/s"
+RAYS = 64
+
+
+# ----------------------------------------------------------------------------- helpers ----
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_scene(workload):
+    from lum_b200 import scenes
+    if workload == "demo":
+        d = scenes.demo_scene()
+        return dict(world=d["world"], bricks=d["bricks"], materials=d["materials"])
+    if workload.startswith("synthetic-"):
+        wx, wy, wz = (int(v) for v in workload.split("-")[1].split("x"))
+        return scenes.synthetic_scene(wx, wy, wz)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cuda_iface(ptr, n):
+    class _A:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+    return _A()
+
+
+# ----------------------------------------------------------------------------- ours -------
+class Runner:
+    """One rank's stage + the per-step sequences (value region and e2e region)."""
+
+    def __init__(self, scene, device, rank, world_size, torch, dist):
+        import lum_b200
+        self.torch, self.dist = torch, dist
+        self.rank, self.n = rank, world_size
+        self.scene = scene
+        wz, wy, wx = scene["world"].shape
+        if wz % world_size:
+            raise SystemExit(f"world z={wz} not divisible by {world_size} ranks")
+        self.z0, self.z1 = wz // world_size * rank, wz // world_size * (rank + 1)
+        self.st = lum_b200.RadianceStage((wx, wy, wz), scene["bricks"].shape[0], rays_per_probe=RAYS, device=device)
+        self.st.upload_world(scene["world"])
+        self.st.upload_bricks(0, scene["bricks"])
+        self.st.upload_materials(scene["materials"])
+        self.nreq = self.st.build_requests()
+        self.cells = wx * wy * wz
+        self.slab_cells = self.cells // world_size
+        self.stream = torch.cuda.ExternalStream(self.st.stream(), device=device)
+        self.field_t = torch.as_tensor(cuda_iface(self.st.field_device_ptr(), self.cells), device=f"cuda:{device}")
+        self.world_host = np.ascontiguousarray(scene["world"], np.int16)
+        self.field_host = np.empty(self.cells, np.uint32)
+        self.zero_field = np.zeros(self.cells, np.uint32)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")   # > 126 MB L2
+
+    def flush_l2(self, k=0):
+        with self.torch.cuda.stream(self.stream):
+            self.flush.fill_(k & 0xFF)
+
+    def reset(self):
+        self.st.upload_field(self.zero_field)
+        self.st.wait_idle()
+
+    def exchange(self):
+        if self.n > 1:
+            with self.torch.cuda.stream(self.stream):
+                shard = self.field_t[self.rank * self.slab_cells:(self.rank + 1) * self.slab_cells]
+                self.dist.all_gather_into_tensor(self.field_t, shard)
+
+    def step_resident(self, seed):
+        if self.n > 1:
+            self.st.update_slab(seed, 1, 0, self.z0, self.z1)
+            self.exchange()
+        else:
+            self.st.update(seed, 1, 0)
+
+    def step_e2e(self, seed):
+        self.st.upload_world(self.world_host)                 # H2D: world (end_blockify/exec_copies)
+        self.st.build_requests()                              # device builder (+8 B count readback)
+        self.step_resident(seed)
+        if self.n > 1:                                        # D2H: each rank reads its slab of the result
+            with self.torch.cuda.stream(self.stream):
+                t = self.field_t[self.rank * self.slab_cells:(self.rank + 1) * self.slab_cells].cpu()
+            return t
+        self.st.download_field(self.field_host)
+        return self.field_host
+
+    def timed(self, fn, steps, warmup, first_seed=0):
+        """W untimed + K timed steps; per-step CUDA events on the stage stream, L2 flushed in
+        between (outside the events); returns (total_ms_max_over_ranks, per_step_ms list)."""
+        torch, dist = self.torch, self.dist
+        self.reset()
+        for i in range(warmup):
+            fn(first_seed + i)
+        with torch.cuda.stream(self.stream):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            torch.cuda.synchronize()
+            if self.n > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            for k in range(steps):
+                self.flush_l2(k)                              # L2 flush on the same stream, outside the events
+                ev[k][0].record(self.stream)
+                fn(first_seed + warmup + k)
+                ev[k][1].record(self.stream)
+            torch.cuda.synchronize()
+            if self.n > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        per = [a.elapsed_time(b) for a, b in ev]
+        total = float(sum(per))
+        if self.n > 1:
+            t = torch.tensor([total], dtype=torch.float64, device=self.field_t.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        return total, per
+
+    def algorithmic_bytes(self, steps, warmup, first_seed=0):
+        """S,H,N of the timed steps from the instrumented kernel variant (untimed pass)."""
+        self.reset()
+        import lum_b200
+        out = []
+        for i in range(warmup + steps):
+            self.st.set_debug(lum_b200.DEBUG_PRE_BLEND if i >= warmup else 0)
+            if self.n > 1:
+                b, e = self.st.slab_range(1, 0, self.z0, self.z1)
+                self.st.update_range(first_seed + i, 1, 0, b, e)
+                nwg = e - b
+                self.exchange()
+            else:
+                self.st.update(first_seed + i, 1, 0)
+                nwg = self.nreq
+            if i >= warmup:
+                S, H, N = self.st.download_debug(nwg, pre_blend=False)["totals"]
+                out.append(3 * S + 52 * H + 12 * N)
+        self.st.set_debug(0)
+        return out
+
+
+def measure(runner, steps, warmup, peak):
+    """value / e2e / roofline for one workload on this rank set."""
+    st = runner.st
+    total_rays = runner.nreq * RAYS
+    # device-resident
+    l0 = st.launch_count()
+    total_ms, per = runner.timed(runner.step_resident, steps, warmup)
+    launches = st.launch_count() - l0 - 0
+    launches_timed = launches * steps // (steps + warmup) if (steps + warmup) else 0
+    ms_per_step = total_ms / steps
+    value = total_rays / (ms_per_step * 1e-3)
+    # per-kernel time (profiling events around the trace kernel) + algorithmic bytes
+    st.set_profiling(True)
+    ks = []
+    runner.reset()
+    for i in range(warmup + steps):
+        runner.flush_l2(i)
+        runner.step_resident(i)
+        if i >= warmup:
+            ks.append(st.last_kernel_ms())
+    st.set_profiling(False)
+    kernel_ms = float(np.mean(ks))
+    ab = runner.algorithmic_bytes(steps, warmup)
+    alg_bytes = float(np.mean(ab))
+    kt = kernel_ms if kernel_ms else ms_per_step
+    achieved = alg_bytes / (kt * 1e-3) / 1e9
+    # end to end
+    e2e_ms, _ = runner.timed(runner.step_e2e, steps, warmup)
+    e2e_value = total_rays / (e2e_ms / steps * 1e-3)
+    world_bytes = runner.world_host.nbytes
+    return dict(value=value, ms_per_step=ms_per_step, per_step_ms=per, kernel_ms=kernel_ms,
+                alg_bytes=alg_bytes, achieved=achieved, frac=achieved / peak,
+                e2e_value=e2e_value, e2e_ms=e2e_ms / steps, h2d=world_bytes,
+                d2h=runner.cells * 4 // runner.n * runner.n + 8, launches=launches_timed,
+                probes=runner.nreq, rays=total_rays)
+
+
+def cpu_baseline(scene, budget_s, threads=0):
+    """The oracle port on the host cores, on a bounded strided sample of the request list."""
+    import oracle as O
+    sc = O.Scene(scene["world"], scene["bricks"], scene["materials"], rays_per_probe=RAYS)
+    req = O.build_requests(scene["world"])
+    f0 = np.zeros(sc.cells, np.uint32)
+    probe = req[:: max(1, len(req) // 2048)][:2048]
+    t0 = time.perf_counter()
+    r = O.update(sc, f0, probe, 1, nthreads=threads)
+    dt = time.perf_counter() - t0
+    rate = len(probe) / max(dt, 1e-6)
+    n = int(min(len(req), max(len(probe), rate * budget_s)))
+    sample = req[:: max(1, len(req) // n)][:n]
+    t0 = time.perf_counter()
+    r = O.update(sc, f0, sample, 1, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return dict(value=len(sample) * RAYS / dt, unit=UNIT, cores=int(r["threads"]), kind="port",
+                sample=f"{len(sample)} of {len(req)} probes (every {max(1, len(req) // n)}-th request, "
+                       f"time_seed 1, zero field), {dt:.2f} s wall, OpenMP over probes"), sample, sc, f0
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port
+    (the reference's own radiance.comp cannot execute here: no Vulkan)."""
+    if rank != 0:
+        return
+    import oracle as O
+    scene = make_scene(args.workload)
+    nsteps = args.steps + args.warmup
+    budget = max(1.0, min(20.0, 150.0 / max(1, nsteps)))
+    base, sample, sc, f0 = cpu_baseline(scene, budget)
+    for i in range(args.warmup):
+        O.update(sc, f0, sample, i)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        O.update(sc, f0, sample, args.warmup + k)
+    dt = time.perf_counter() - t0
+    value = len(sample) * RAYS * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": args.workload, "rays_per_probe": RAYS,
+                                            "sample_probes": int(len(sample))},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": base["cores"], "kind": "port",
+                             "sample": base["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world_size):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    peak, peak_src = load_peaks()
+    scene = make_scene(args.workload)
+    runner = Runner(scene, local_rank, rank, world_size, torch, dist)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    m = measure(runner, args.steps, args.warmup, peak)
+    clocks = sampler.stop() if rank == 0 else None
+    extra = {}
+    if rank == 0 and world_size == 1 and args.workload != "demo" and not args.no_demo:
+        dr = Runner(make_scene("demo"), local_rank, 0, 1, torch, dist)
+        dm = measure(dr, max(args.steps, 20), max(args.warmup, 5), peak)
+        extra["demo"] = {"workload": "demo (BASELINE configs[1]: 48x48x16 demo world, full recompute)",
+                         "probes": dm["probes"], "rays": dm["rays"], "value": dm["value"], "unit": UNIT,
+                         "ms_per_step": dm["ms_per_step"], "kernel_ms": dm["kernel_ms"],
+                         "e2e": {"value": dm["e2e_value"], "unit": UNIT, "ms_per_step": dm["e2e_ms"],
+                                 "h2d_bytes_per_step": dm["h2d"], "d2h_bytes_per_step": dm["d2h"]},
+                         "roofline": {"bound": "hbm", "achieved": dm["achieved"], "peak": peak, "unit": "GB/s",
+                                      "frac": dm["frac"], "traffic": None}}
+    if rank == 0:
+        cb = None
+        if world_size == 1 and not args.no_cpu:
+            cb = cpu_baseline(scene, 12.0)[0]
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world_size,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": RAYS,
+                           "rays_per_step": m["rays"], "parallelism": f"probe z-slabs x{world_size} + field all-gather"
+                           if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
+                           "time_seed": "step index", "initial_field": "zero"},
+                "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"],
+                        "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+                "gpu_launches": m["launches"],
+                "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
+                             "frac": m["frac"], "traffic": None, "peak_source": peak_src,
+                             "kernel": "radiance_update kernel", "kernel_ms": m["kernel_ms"],
+                             "algorithmic_bytes_per_launch": m["alg_bytes"]},
+                "clocks": clocks}
+        if cb:
+            line["cpu_baseline"] = cb
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="synthetic-256x256x64")
+    ap.add_argument("--no-demo", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world_size != args.gpus:
+        if args.gpus > 1 and world_size == 1:
+            raise SystemExit("for --gpus N>1 launch with torch.distributed.run --nproc-per-node N")
+    run_ours(args, rank, local_rank, world_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,11 +127,21 @@ int lumcu_set_debug(LumcuCtx *ctx, int32_t flags);
 int lumcu_download_debug(LumcuCtx *ctx, float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
                          uint64_t totals[3]);
 
+/* Self-test hook: the device's unorm10 -> float conversion for all 1024 codes (the kernel computes
+ * c/1023 with a reciprocal + one FMA correction step; tests compare this table bit-for-bit with
+ * IEEE division).  out: 1024 floats. */
+int lumcu_debug_unpack_table(LumcuCtx *ctx, float *out);
+
 /* vkDeviceWaitIdle for this stage. */
 int lumcu_wait_idle(LumcuCtx *ctx);
 /* GPU time of the last update, the pair of timestamps around vkCmdDispatch
  * (internal_render.cpp:1205-1207, :2173 timeTakenByRadiance). */
 int lumcu_last_update_ms(LumcuCtx *ctx, float *ms);
+/* Per-kernel timing for roofline reports: while on, an extra event pair brackets the ray-march
+ * kernel alone (the commit / exchange are outside it); lumcu_last_kernel_ms returns its duration
+ * for the last update.  Off by default (the pair costs ~2 us per update). */
+int lumcu_set_profiling(LumcuCtx *ctx, int32_t on);
+int lumcu_last_kernel_ms(LumcuCtx *ctx, float *ms);
 /* Number of kernels this library launched on the context so far. */
 int lumcu_launch_count(LumcuCtx *ctx, uint64_t *count);
 

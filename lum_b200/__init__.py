@@ -55,8 +55,11 @@ SYMBOLS = {
     "lumcu_direction_table": (C.c_int, [_P, _P]),
     "lumcu_set_debug": (C.c_int, [_P, C.c_int32]),
     "lumcu_download_debug": (C.c_int, [_P, _P, _P, _P, _P]),
+    "lumcu_debug_unpack_table": (C.c_int, [_P, _P]),
     "lumcu_wait_idle": (C.c_int, [_P]),
     "lumcu_last_update_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "lumcu_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "lumcu_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lumcu_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "lumcu_field_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "lumcu_world_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
@@ -200,12 +203,25 @@ class RadianceStage:
         self._ck(self.lib.lumcu_download_debug(self.ctx, _ptr(pre), _ptr(rs), _ptr(rh), tot))
         return dict(pre_blend=pre, ray_samples=rs, ray_hits=rh, totals=(int(tot[0]), int(tot[1]), int(tot[2])))
 
+    def debug_unpack_table(self):
+        out = np.zeros(1024, np.float32)
+        self._ck(self.lib.lumcu_debug_unpack_table(self.ctx, _ptr(out)))
+        return out
+
     def wait_idle(self):
         self._ck(self.lib.lumcu_wait_idle(self.ctx))
 
     def last_update_ms(self):
         ms = C.c_float()
         self._ck(self.lib.lumcu_last_update_ms(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on):
+        self._ck(self.lib.lumcu_set_profiling(self.ctx, int(bool(on))))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.lumcu_last_kernel_ms(self.ctx, C.byref(ms)))
         return ms.value
 
     def launch_count(self):

@@ -78,8 +78,8 @@ struct LumcuCtx {
     long long cells = 0;
     long long max_requests = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    bool timed = false;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    bool timed = false, profiling = false, ktimed = false;
 
     int16_t *d_world = nullptr;
     uint8_t *d_bricks = nullptr;
@@ -95,6 +95,7 @@ struct LumcuCtx {
     long long nreq = 0;          // current request count
     long long nsorted = 0;       // leading requests known to be z-sorted
     bool have_world = false, have_bricks = false, have_materials = false;
+    bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
 
     // builder scratch (lazy)
     uint8_t *d_flags = nullptr;
@@ -190,7 +191,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         return fail(LUMCU_E_ARG, "workgroup range [%lld,%lld) outside [0,%lld)", wg_begin, wg_end, nwg_all);
     const long long nwg = wg_end - wg_begin;
     if (nwg > 0) {
-        SceneView sv{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity};
+        SceneView sv{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity, c->brick0_empty ? 1 : 0};
         UpdateArgs a{};
         a.requests = c->d_requests;
         a.dir_table = c->d_table;
@@ -210,7 +211,9 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             if (int rc = launch_update_R<true>(c, sv, a, nwg)) return rc;
             c->dbg_nwg = nwg; c->dbg_wg_begin = wg_begin;
         } else {
+            if (c->profiling) CU(cudaEventRecord(c->ev_k0, c->stream));
             if (int rc = launch_update_R<false>(c, sv, a, nwg)) return rc;
+            if (c->profiling) { CU(cudaEventRecord(c->ev_k1, c->stream)); c->ktimed = true; }
         }
         const int ct = 256;
         commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
@@ -260,6 +263,8 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaEventCreate(&c->ev_begin));
     CUB(cudaEventCreate(&c->ev_end));
+    CUB(cudaEventCreate(&c->ev_k0));
+    CUB(cudaEventCreate(&c->ev_k1));
     CUB(cudaMalloc(&c->d_world, (size_t)c->cells * sizeof(int16_t)));
     CUB(cudaMalloc(&c->d_bricks, (size_t)d->palette_capacity * 4096));
     CUB(cudaMalloc(&c->d_materials, 256 * 6 * sizeof(float)));
@@ -296,6 +301,8 @@ int lumcu_destroy(LumcuCtx *c) {
     c->stage_world.release(); c->stage_req.release(); c->stage_misc.release();
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+    if (c->ev_k1) cudaEventDestroy(c->ev_k1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -322,8 +329,14 @@ int lumcu_upload_bricks(LumcuCtx *c, int32_t first, int32_t count, const uint8_t
     if (int rc = use(c)) return rc;
     if (!vox || count < 0 || first < 0 || first + count > c->desc.palette_capacity)
         return fail(LUMCU_E_ARG, "brick range [%d,%d) outside palette capacity %d", first, first + count, c->desc.palette_capacity);
-    if (count > 0)
+    if (count > 0) {
         if (int rc = staged_upload(c, c->stage_misc, c->d_bricks + (size_t)first * 4096, vox, (size_t)count * 4096)) return rc;
+        if (first == 0) {
+            bool empty = true;
+            for (int i = 0; i < 4096 && empty; i++) empty = vox[i] == 0;
+            c->brick0_empty = empty;
+        }
+    }
     c->have_bricks = true;
     return 0;
 }
@@ -535,6 +548,20 @@ int lumcu_download_debug(LumcuCtx *c, float *pre_blend, uint32_t *ray_samples, u
     return 0;
 }
 
+int lumcu_debug_unpack_table(LumcuCtx *c, float *out) {
+    if (int rc = use(c)) return rc;
+    if (!out) return fail(LUMCU_E_ARG, "null argument");
+    float *d = nullptr;
+    CU(cudaMalloc(&d, 1024 * sizeof(float)));
+    unpack_table_kernel<<<4, 256, 0, c->stream>>>(d);
+    c->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, d, 1024 * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(LUMCU_E_CUDA, "unpack table: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 int lumcu_wait_idle(LumcuCtx *c) {
     if (int rc = use(c)) return rc;
     CU(cudaStreamSynchronize(c->stream));
@@ -547,6 +574,21 @@ int lumcu_last_update_ms(LumcuCtx *c, float *ms) {
     if (!c->timed) return fail(LUMCU_E_STATE, "no update has run");
     CU(cudaEventSynchronize(c->ev_end));
     CU(cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return 0;
+}
+
+int lumcu_set_profiling(LumcuCtx *c, int32_t on) {
+    if (!c) return fail(LUMCU_E_ARG, "null context");
+    c->profiling = on != 0;
+    return 0;
+}
+
+int lumcu_last_kernel_ms(LumcuCtx *c, float *ms) {
+    if (int rc = use(c)) return rc;
+    if (!ms) return fail(LUMCU_E_ARG, "null argument");
+    if (!c->ktimed) return fail(LUMCU_E_STATE, "no profiled update has run (lumcu_set_profiling first)");
+    CU(cudaEventSynchronize(c->ev_k1));
+    CU(cudaEventElapsedTime(ms, c->ev_k0, c->ev_k1));
     return 0;
 }
 

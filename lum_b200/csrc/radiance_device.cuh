@@ -20,6 +20,7 @@ struct SceneView {
     const uint32_t *__restrict__ field;     // [z][y][x] packed A2B10G10R10 (read side)
     int wx, wy, wz;
     int capacity;                           // bricks addressable
+    int brick0_empty;                       // brick 0 is all zeros (always, unless the user loaded a block 0)
 };
 
 struct f3 { float x, y, z; };
@@ -53,15 +54,24 @@ __device__ __forceinline__ int get_voxel(const SceneView &s, int ix, int iy, int
     if ((unsigned)bx < (unsigned)s.wx && (unsigned)by < (unsigned)s.wy && (unsigned)bz < (unsigned)s.wz)
         id = __ldg(s.world + (bx + s.wx * (by + s.wy * bz)));
     int v = 0;
-    if ((unsigned)id < (unsigned)s.capacity)
+    if ((unsigned)id < (unsigned)s.capacity && !(id == 0 && s.brick0_empty))
         v = __ldg(s.bricks + ((size_t)id * 4096u + (size_t)(((ix & 15) << 8) | ((iy & 15) << 4) | (iz & 15))));
     block_id = id;
     return v;
 }
 
+// c/1023 correctly rounded without the division subroutine: q0 = c*RN(1/1023), one Markstein
+// correction step with explicit FMAs.  Bit-identical to IEEE c/1023.0f for every c in [0,1023]
+// (verified exhaustively; tests/test_parity_gpu.py::test_unpack_all_codes).
+__device__ __forceinline__ float unorm10_to_float(uint32_t c) {
+    const float r = 1.0f / 1023.0f;
+    float fc = (float)c;
+    float q0 = fc * r;
+    float rem = __fmaf_rn(-1023.0f, q0, fc);
+    return __fmaf_rn(rem, r, q0);
+}
 __device__ __forceinline__ f3 unpack10(uint32_t w) {
-    return {(float)(w & 1023u) / 1023.0f, (float)((w >> 10) & 1023u) / 1023.0f,
-            (float)((w >> 20) & 1023u) / 1023.0f};
+    return {unorm10_to_float(w & 1023u), unorm10_to_float((w >> 10) & 1023u), unorm10_to_float((w >> 20) & 1023u)};
 }
 __device__ __forceinline__ uint32_t unorm10(float v) {
     float c = gmin(gmax(v, 0.0f), 1.0f);
@@ -72,7 +82,13 @@ __device__ __forceinline__ uint32_t pack10(float r, float g, float b) {
     return unorm10(r) | (unorm10(g) << 10) | (unorm10(b) << 20) | (3u << 30);
 }
 
-__device__ __forceinline__ int wrapi(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+// REPEAT wrap of a texel index.  Hits lie inside the world, so i is within one period of [0,n)
+// except for degenerate rays; the integer modulo only runs for those.
+__device__ __forceinline__ int wrapi(int i, int n) {
+    if (i < 0) i += n; else if (i >= n) i -= n;
+    if ((unsigned)i >= (unsigned)n) { i %= n; if (i < 0) i += n; }
+    return i;
+}
 __device__ __forceinline__ f3 lerp3(f3 a, f3 b, float w) {
     return {a.x + w * (b.x - a.x), a.y + w * (b.y - a.y), a.z + w * (b.z - a.z)};
 }
@@ -148,6 +164,7 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
         if (p.x < 0.0f || p.y < 0.0f || p.z < 0.0f || p.x >= wsx || p.y >= wsy || p.z >= wsz) break;
         if (t >= 128.0f) break;
     }
+    __syncwarp();   // reconverge before the long hit/miss tail (otherwise early leavers run it in separate passes)
 
     RayResult res;
     if (voxel != 0) {
@@ -157,7 +174,7 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
         int stx = d.x > 0.0f ? 1 : -1, sty = d.y > 0.0f ? 1 : -1, stz = d.z > 0.0f ? 1 : -1;
         float c1x = (floorf(h.x) - h.x) / d.x, c1y = (floorf(h.y) - h.y) / d.y, c1z = (floorf(h.z) - h.z) / d.z;
         f3 tMax = {gmax(c1x, c1x + inv.x), gmax(c1y, c1y + inv.y), gmax(c1z, c1z + inv.z)};
-        f3 tDelta = {1.0f / fabsf(d.x), 1.0f / fabsf(d.y), 1.0f / fabsf(d.z)};
+        f3 tDelta = {fabsf(inv.x), fabsf(inv.y), fabsf(inv.z)};   // 1/|d| == |1/d| exactly
         int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
         float ax = 0.0f, ay = 0.0f, az = 0.0f;
         int id;

@@ -110,6 +110,11 @@ __global__ void shift_kernel(uint32_t *__restrict__ field, const uint32_t *__res
         field[i] = tmp[sx + wx * (sy + (long long)wy * sz)];
 }
 
+__global__ void unpack_table_kernel(float *__restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < 1024) out[c] = unorm10_to_float((uint32_t)c);
+}
+
 // ---- request-list builder (internal_render.cpp:1142-1169) ------------------------------
 constexpr int BUILD_THREADS = 256;
 

@@ -50,6 +50,15 @@ def test_direction_table_matches_oracle(oracle_mod, demo):
     assert np.array_equal(bits(st.direction_table()), bits(oracle_mod.direction_table(64)))
 
 
+def test_unpack_all_codes(oracle_mod, demo):
+    """unorm10 -> float on the device (reciprocal + FMA correction) == IEEE c/1023 for all codes."""
+    st = make_stage(demo)
+    exp = (np.arange(1024, dtype=np.float32) / np.float32(1023.0)).astype(np.float32)
+    assert np.array_equal(bits(st.debug_unpack_table()), bits(exp))
+    for c in (0, 1, 511, 512, 1022, 1023):
+        assert oracle_mod.unpack(c)[0] == exp[c]
+
+
 def test_demo_single_update_config1(oracle_mod, demo):
     """BASELINE config 1/2: demo world, all 2,689 probes x 64 rays, time_seed 1, zero field."""
     O = oracle_mod
