@@ -58,6 +58,7 @@ SYMBOLS = {
     "lumcu_debug_unpack_table": (C.c_int, [_P, _P]),
     "lumcu_wait_idle": (C.c_int, [_P]),
     "lumcu_last_update_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "lumcu_set_kernel_variant": (C.c_int, [_P, C.c_int32]),
     "lumcu_set_profiling": (C.c_int, [_P, C.c_int32]),
     "lumcu_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lumcu_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
@@ -215,6 +216,9 @@ class RadianceStage:
         ms = C.c_float()
         self._ck(self.lib.lumcu_last_update_ms(self.ctx, C.byref(ms)))
         return ms.value
+
+    def set_kernel_variant(self, variant):
+        self._ck(self.lib.lumcu_set_kernel_variant(self.ctx, int(variant)))
 
     def set_profiling(self, on):
         self._ck(self.lib.lumcu_set_profiling(self.ctx, int(bool(on))))

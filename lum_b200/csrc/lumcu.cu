@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -95,6 +96,9 @@ struct LumcuCtx {
     long long nreq = 0;          // current request count
     long long nsorted = 0;       // leading requests known to be z-sorted
     bool have_world = false, have_bricks = false, have_materials = false;
+    int pool_threads = 128;      // tuning knobs (env LUMCU_POOL_THREADS / LUMCU_CARVEOUT, read at create)
+    int carveout = -1;
+    int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
     bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
 
     // builder scratch (lazy)
@@ -151,6 +155,32 @@ void host_direction_table(int n, std::vector<float> &out) {
     }
 }
 
+// production path: pooled kernel (no z filter); one CTA per 4*threads rays
+template <int R, int T, bool DEBUG>
+int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
+    constexpr int ppc = 4 * T / R;
+    auto k = radiance_update_pool_kernel<R, T, DEBUG>;
+    if (c->carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout);
+    dim3 grid((unsigned)((nwg + ppc - 1) / ppc));
+    k<<<grid, T, 0, c->stream>>>(sv, a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <bool DEBUG>
+int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
+    switch (c->R) {
+        case 16: return launch_pool_one<16, 256, DEBUG>(c, sv, a, nwg);
+        case 32: return launch_pool_one<32, 256, DEBUG>(c, sv, a, nwg);
+        case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, DEBUG>(c, sv, a, nwg)
+                                               : launch_pool_one<64, 256, DEBUG>(c, sv, a, nwg);
+        case 128: return launch_pool_one<128, 256, DEBUG>(c, sv, a, nwg);
+        case 256: return launch_pool_one<256, 256, DEBUG>(c, sv, a, nwg);
+        default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);
+    }
+}
+
 template <bool DEBUG>
 int launch_update_R(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
     dim3 grid((unsigned)nwg);
@@ -201,6 +231,10 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         a.z_begin = z_begin; a.z_end = z_end;
         a.reactiveness = c->desc.reactiveness;
         a.sun_x = c->sun[0]; a.sun_y = c->sun[1]; a.sun_z = c->sun[2];
+        // the z filter (unsorted special tail of a slab update) only exists in the per-workgroup kernel
+        // and small dispatches (demo-sized worlds) are latency-bound: they want one workgroup per CTA
+        const bool unfiltered = z_begin <= -32768 && z_end >= 32768;
+        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && nwg * c->R >= (1ll << 19)));
         if (c->debug_flags) {
             if (int rc = ensure_debug(c)) return rc;
             a.dbg_pre_blend = (c->debug_flags & LUMCU_DEBUG_PRE_BLEND) ? c->d_pre_blend : nullptr;
@@ -208,11 +242,11 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             a.dbg_hits = (c->debug_flags & LUMCU_DEBUG_RAYS) ? c->d_ray_hits : nullptr;
             a.dbg_totals = c->d_totals;
             CU(cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
-            if (int rc = launch_update_R<true>(c, sv, a, nwg)) return rc;
+            if (int rc = (use_pool ? launch_update_pool<true>(c, sv, a, nwg) : launch_update_R<true>(c, sv, a, nwg))) return rc;
             c->dbg_nwg = nwg; c->dbg_wg_begin = wg_begin;
         } else {
             if (c->profiling) CU(cudaEventRecord(c->ev_k0, c->stream));
-            if (int rc = launch_update_R<false>(c, sv, a, nwg)) return rc;
+            if (int rc = (use_pool ? launch_update_pool<false>(c, sv, a, nwg) : launch_update_R<false>(c, sv, a, nwg))) return rc;
             if (c->profiling) { CU(cudaEventRecord(c->ev_k1, c->stream)); c->ktimed = true; }
         }
         const int ct = 256;
@@ -276,6 +310,9 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaMemsetAsync(c->d_bricks, 0, (size_t)d->palette_capacity * 4096, c->stream));
     CUB(cudaMemsetAsync(c->d_materials, 0, 256 * 6 * sizeof(float), c->stream));
     CUB(cudaMemsetAsync(c->d_field, 0, (size_t)c->cells * sizeof(uint32_t), c->stream));   // initial field = zero words
+    if (const char *e = getenv("LUMCU_POOL_THREADS")) c->pool_threads = atoi(e) == 256 ? 256 : 128;
+    if (const char *e = getenv("LUMCU_CARVEOUT")) c->carveout = atoi(e);
+    if (const char *e = getenv("LUMCU_KERNEL_VARIANT")) c->kernel_variant = atoi(e);
     host_direction_table(R, c->h_table);
     CUB(cudaMemcpyAsync(c->d_table, c->h_table.data(), (size_t)R * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     {   // normalize(vec3(0.5,0.5,-0.9)) (radiance.comp:42), f32, x->y->z dot
@@ -574,6 +611,13 @@ int lumcu_last_update_ms(LumcuCtx *c, float *ms) {
     if (!c->timed) return fail(LUMCU_E_STATE, "no update has run");
     CU(cudaEventSynchronize(c->ev_end));
     CU(cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return 0;
+}
+
+int lumcu_set_kernel_variant(LumcuCtx *c, int32_t variant) {
+    if (!c) return fail(LUMCU_E_ARG, "null context");
+    if (variant < 0 || variant > 2) return fail(LUMCU_E_ARG, "unknown kernel variant %d", variant);
+    c->kernel_variant = variant;
     return 0;
 }
 

@@ -121,54 +121,56 @@ struct RayResult {
     int hit;
 };
 
-// Ray setup (radiance.comp:370-381) + trace_ray (:316-347) + CastRay_fast (:183-291).
+// ---- ray setup (radiance.comp:370-381) ---------------------------------------------------
 // gid_x = gl_GlobalInvocationID.x, ray = gid_x % R, fib = direction table entry of `ray`.
-__device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px, int py, int pz,
-                                                     uint32_t gid_x, int ray, f3 fib, int time_seed,
-                                                     f3 sun) {
+// Outputs origin o, direction d and inv = 1/d (radiance.comp:198).
+__device__ __forceinline__ void setup_ray(int px, int py, int pz, uint32_t gid_x, int ray, f3 fib,
+                                          int time_seed, f3 &o, f3 &d, f3 &inv) {
     uint32_t sx = gid_x + (uint32_t)time_seed, sy = (uint32_t)time_seed, sz = (uint32_t)time_seed;
     f3 r1 = hash33(sx, sy, sz);
     f3 r2 = hash33(sx + 1u, sy, sz);
     f3 j = {fib.x + 0.1f * ((r1.x - 0.5f) * 2.0f), fib.y + 0.1f * ((r1.y - 0.5f) * 2.0f),
             fib.z + 0.1f * ((r1.z - 0.5f) * 2.0f)};
     float len = sqrtf(j.x * j.x + j.y * j.y + j.z * j.z);
-    f3 d = {j.x / len, j.y / len, j.z / len};
-    f3 o = {(float)px * 16.0f + 8.0f, (float)py * 16.0f + 8.0f, (float)pz * 16.0f + 8.0f};
+    d = {j.x / len, j.y / len, j.z / len};
+    o = {(float)px * 16.0f + 8.0f, (float)py * 16.0f + 8.0f, (float)pz * 16.0f + 8.0f};
     o.x += d.x * 6.0f; o.y += d.y * 6.0f; o.z += d.z * 6.0f;
     o.x += (r2.x - 0.5f) * 2.0f; o.y += (r2.y - 0.5f) * 2.0f; o.z += (r2.z - 0.5f) * 2.0f;
     if (ray & 1) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
+    inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+}
 
-    // ---- coarse march (radiance.comp:198-244) ----
-    const f3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
-    const f3 corner = {d.x > 0.0f ? 16.0f : 0.0f, d.y > 0.0f ? 16.0f : 0.0f, d.z > 0.0f ? 16.0f : 0.0f};
-    const float wsx = (float)s.wx * 16.0f, wsy = (float)s.wy * 16.0f, wsz = (float)s.wz * 16.0f;
-    float t = 0.0f;
-    int voxel = 0, samples = 0;
-    for (;;) {
-        t += 0.5f;
-        f3 p = {o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
-        int ix = f2i(p.x), iy = f2i(p.y), iz = f2i(p.z);
-        int id;
-        voxel = get_voxel(s, ix, iy, iz, id);
-        samples++;
-        if (id == 0) {
-            float bx = (float)(sdiv16(ix) * 16) + corner.x;
-            float by = (float)(sdiv16(iy) * 16) + corner.y;
-            float bz = (float)(sdiv16(iz) * 16) + corner.z;
-            float ex = bx * inv.x + (-p.x * inv.x);
-            float ey = by * inv.y + (-p.y * inv.y);
-            float ez = bz * inv.z + (-p.z * inv.z);
-            t += gmax(gmin(ex, gmin(ey, ez)), 0.01f);
-        }
-        if (voxel != 0) break;
-        if (p.x < 0.0f || p.y < 0.0f || p.z < 0.0f || p.x >= wsx || p.y >= wsy || p.z >= wsz) break;
-        if (t >= 128.0f) break;
+// ---- one iteration of the coarse march (radiance.comp:205-244) ----------------------------
+// Advances t; returns 0 = keep marching, 1 = hit (voxel != 0), 2 = miss (left the world or t >= 128).
+struct MarchConsts { float wsx, wsy, wsz; };
+__device__ __forceinline__ int march_step(const SceneView &s, const MarchConsts &mc, const f3 &o, const f3 &d,
+                                          const f3 &inv, float &t) {
+    t += 0.5f;
+    f3 p = {o.x + d.x * t, o.y + d.y * t, o.z + d.z * t};
+    int ix = f2i(p.x), iy = f2i(p.y), iz = f2i(p.z);
+    int id;
+    int voxel = get_voxel(s, ix, iy, iz, id);
+    if (id == 0) {
+        float bx = (float)(sdiv16(ix) * 16) + (d.x > 0.0f ? 16.0f : 0.0f);
+        float by = (float)(sdiv16(iy) * 16) + (d.y > 0.0f ? 16.0f : 0.0f);
+        float bz = (float)(sdiv16(iz) * 16) + (d.z > 0.0f ? 16.0f : 0.0f);
+        float ex = bx * inv.x + (-p.x * inv.x);
+        float ey = by * inv.y + (-p.y * inv.y);
+        float ez = bz * inv.z + (-p.z * inv.z);
+        t += gmax(gmin(ex, gmin(ey, ez)), 0.01f);
     }
-    __syncwarp();   // reconverge before the long hit/miss tail (otherwise early leavers run it in separate passes)
+    if (voxel != 0) return 1;
+    if (p.x < 0.0f || p.y < 0.0f || p.z < 0.0f || p.x >= mc.wsx || p.y >= mc.wsy || p.z >= mc.wsz) return 2;
+    if (t >= 128.0f) return 2;
+    return 0;
+}
 
-    RayResult res;
-    if (voxel != 0) {
-        // ---- refinement (radiance.comp:246-288) ----
+// ---- after the march: refinement + hit shading, or sky (radiance.comp:246-288,316-347) ----
+// t = fraction at loop exit; hit = CastRay_fast's return value.  refine_samples counts GetVoxel calls.
+__device__ __forceinline__ f3 finish_ray(const SceneView &s, const f3 &o, const f3 &d, const f3 &inv, float t,
+                                         bool hit, f3 sun, int &refine_samples) {
+    refine_samples = 0;
+    if (hit) {
         float tb = t - 1.5f;
         f3 h = {o.x + d.x * tb, o.y + d.y * tb, o.z + d.z * tb};
         int stx = d.x > 0.0f ? 1 : -1, sty = d.y > 0.0f ? 1 : -1, stz = d.z > 0.0f ? 1 : -1;
@@ -179,7 +181,7 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
         float ax = 0.0f, ay = 0.0f, az = 0.0f;
         int id;
         int vid = get_voxel(s, vx, vy, vz, id);
-        samples++;
+        int ns = 1;
         int it = 0;
         while ((it++ <= 4) && (vid == 0)) {
             ax = ((tMax.x <= tMax.y) && (tMax.x <= tMax.z)) ? 1.0f : 0.0f;
@@ -188,35 +190,48 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
             vx += stx * (int)ax; vy += sty * (int)ay; vz += stz * (int)az;
             tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
             vid = get_voxel(s, vx, vy, vz, id);
-            samples++;
+            ns++;
         }
+        refine_samples = ns;
         f3 n = {-((float)stx * ax), -((float)sty * ay), -((float)stz * az)};
         float tf = (tMax.x - tDelta.x) * ax + (tMax.y - tDelta.y) * ay + (tMax.z - tDelta.z) * az;
         const float *m = s.materials + 6 * (vid & 255);
         float mr = __ldg(m), mg = __ldg(m + 1), mb = __ldg(m + 2), me = __ldg(m + 4);
-        // ---- shade hit (radiance.comp:331-333,161-166) ----
         f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
         f3 bp = {(x.x + n.x * 16.0f) / 16.0f, (x.y + n.y * 16.0f) / 16.0f, (x.z + n.z * 16.0f) / 16.0f};
         f3 g = gather_field(s, bp);
-        res.light = {0.0f + (1.0f * g.x * mr + mr * me), 0.0f + (1.0f * g.y * mg + mg * me),
-                     0.0f + (1.0f * g.z * mb + mb * me)};
-        res.hit = 1;
-    } else {
-        // ---- sky (radiance.comp:334-344) ----
-        float glp = -(d.x * sun.x + d.y * sun.y + d.z * sun.z);
-        f3 l = {0.0f, 0.0f, 0.0f};
-        if (glp > 0.95f) {
-            l.x += 1.0f * glp * (0.9f * 3.0f);
-            l.y += 1.0f * glp * (0.9f * 3.0f);
-            l.z += 1.0f * glp * (0.6f * 3.0f);
-        }
-        l.x += 1.0f * (0.53f * 0.1f);
-        l.y += 1.0f * (0.81f * 0.1f);
-        l.z += 1.0f * (0.92f * 0.1f);
-        res.light = l;
-        res.hit = 0;
+        return {0.0f + (1.0f * g.x * mr + mr * me), 0.0f + (1.0f * g.y * mg + mg * me),
+                0.0f + (1.0f * g.z * mb + mb * me)};
     }
-    res.samples = samples;
+    float glp = -(d.x * sun.x + d.y * sun.y + d.z * sun.z);
+    f3 l = {0.0f, 0.0f, 0.0f};
+    if (glp > 0.95f) {
+        l.x += 1.0f * glp * (0.9f * 3.0f);
+        l.y += 1.0f * glp * (0.9f * 3.0f);
+        l.z += 1.0f * glp * (0.6f * 3.0f);
+    }
+    l.x += 1.0f * (0.53f * 0.1f);
+    l.y += 1.0f * (0.81f * 0.1f);
+    l.z += 1.0f * (0.92f * 0.1f);
+    return l;
+}
+
+// Whole ray, one thread (the one-workgroup-per-CTA kernel).
+__device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px, int py, int pz,
+                                                     uint32_t gid_x, int ray, f3 fib, int time_seed,
+                                                     f3 sun) {
+    f3 o, d, inv;
+    setup_ray(px, py, pz, gid_x, ray, fib, time_seed, o, d, inv);
+    const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
+    float t = 0.0f;
+    int samples = 0, st;
+    do { st = march_step(s, mc, o, d, inv, t); samples++; } while (st == 0);
+    __syncwarp();   // reconverge before the long tail (early leavers would run it in separate passes)
+    RayResult res;
+    int nr;
+    res.light = finish_ray(s, o, d, inv, t, st == 1, sun, nr);
+    res.hit = st == 1;
+    res.samples = samples + nr;
     return res;
 }
 

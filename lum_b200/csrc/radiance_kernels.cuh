@@ -85,6 +85,244 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
     }
 }
 
+// ---- pooled kernel: the production path ---------------------------------------------------
+// One CTA owns a batch of NR = 4*THREADS rays (NR/R probes) staged in shared memory:
+//   A  ray setup, one ray per thread per round, fully convergent.
+//   B  coarse march with lane-level dynamic refill from the CTA's ray pool: a lane whose ray
+//      ended immediately takes the next ray, so warps stay ~90 % full although ray lengths vary
+//      8x.  When the pool is empty and a warp is down to < PARK live lanes it parks its unfinished
+//      rays (their t goes back to the slot) and leaves.
+//   B' the parked stragglers (~10 % of the rays, the long ones) are compacted into a few "tail"
+//      warps, which march them in further passes among themselves (named barrier), while
+//   C  every other warp already runs refinement + shading on the finished rays, 32 slots per
+//      claim, convergent again.  The tail warps join C when they are done and finally shade the
+//      stragglers.  So nobody idles behind the longest ray of the batch.
+//   D  the workgroup reduction of radiance.comp:386-413 (xor butterfly per 32-ray subgroup) and
+//      store_probe; one warp per probe.
+// The result does not depend on the schedule: each ray's sample sequence is a function of its
+// own (o, d, t) only, and the reduction tree is fixed.
+struct PoolRay { f3 o, d, inv; float t; int ns; };
+
+template <int NR, bool DEBUG>
+struct PoolShared {
+    float o[3][NR], d[3][NR], inv[3][NR], t[NR];
+    unsigned char done[NR];               // 1 = terminated during pass 0 (shaded by the chunk loop)
+    unsigned short ns[DEBUG ? NR : 1];    // marching samples so far (instrumented variant only)
+    __device__ __forceinline__ void load(int r, PoolRay &q) const {
+        q.o = {o[0][r], o[1][r], o[2][r]};
+        q.d = {d[0][r], d[1][r], d[2][r]};
+        q.inv = {inv[0][r], inv[1][r], inv[2][r]};
+        q.t = t[r];
+        if constexpr (DEBUG) q.ns = ns[r];
+    }
+};
+
+// March rays taken from pool positions [0, limit) (slot = src ? src[pos] : pos) until the pool is
+// empty; then either finish the warp's remaining rays (can_park == false) or park them into
+// dst[] (count in *dst_count) once fewer than PARK lanes are live.
+template <int NR, int PARK, bool DEBUG>
+__device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const SceneView &s, const MarchConsts &mc,
+                                           int *next, const unsigned short *src, int limit,
+                                           unsigned short *dst, int *dst_count, bool can_park, bool mark_done,
+                                           int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    int cur = -1;
+    PoolRay q = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, 0.0f, 0};
+    bool exhausted = false;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, cur < 0);
+        if (idle) {
+            if (!exhausted) {
+                const int cnt = __popc(idle);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(next, cnt);
+                base = __shfl_sync(FULL, base, 0);
+                if (cur < 0) {
+                    const int pos = base + __popc(idle & ((1u << lane) - 1u));
+                    if (pos < limit) {
+                        cur = src ? (int)src[pos] : pos;
+                        sm.load(cur, q);
+                    }
+                }
+                exhausted = base + cnt >= limit;
+                idle = __ballot_sync(FULL, cur < 0);
+            }
+            if (exhausted) {
+                const int act = 32 - __popc(idle);
+                if (act == 0) break;
+                if (can_park && act < PARK) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(dst_count, act);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (cur >= 0) {
+                        dst[base + __popc(~idle & ((1u << lane) - 1u))] = (unsigned short)cur;
+                        sm.t[cur] = q.t;
+                        if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
+                    }
+                    break;
+                }
+            }
+        }
+        if (cur >= 0) {
+            const int st = march_step(s, mc, q.o, q.d, q.inv, q.t);
+            q.ns++;
+            if (st) {
+                sm.t[cur] = st == 1 ? q.t : -q.t;                  // sign = miss (t >= 0.5 always)
+                if (mark_done) sm.done[cur] = 1;
+                if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
+                cur = -1;
+            }
+        }
+    }
+}
+
+// Refinement + shading of slot r; the slot's o[] is replaced by the ray's light.
+template <int NR, int R, bool DEBUG>
+__device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const SceneView &s, const UpdateArgs &a,
+                                           long long wg0, int r, f3 sun, unsigned long long &my_s,
+                                           unsigned long long &my_h) {
+    PoolRay q;
+    sm.load(r, q);
+    const bool hit = q.t > 0.0f;
+    int nr;
+    const f3 l = finish_ray(s, q.o, q.d, q.inv, fabsf(q.t), hit, sun, nr);
+    sm.o[0][r] = l.x; sm.o[1][r] = l.y; sm.o[2][r] = l.z;
+    if constexpr (DEBUG) {
+        const unsigned nsamp = (unsigned)q.ns + (unsigned)nr;
+        if (a.dbg_samples) a.dbg_samples[wg0 * R + r] = nsamp;
+        if (a.dbg_hits) a.dbg_hits[wg0 * R + r] = hit ? 1 : 0;
+        my_s += nsamp; my_h += hit ? 1 : 0;
+    }
+}
+
+template <int R, int THREADS, bool DEBUG>
+__global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView s, UpdateArgs a) {
+    constexpr int NR = 4 * THREADS;          // rays per batch
+    constexpr int PPC = NR / R;              // probes per CTA
+    constexpr int NW = THREADS / 32;
+    constexpr int PARK = 16;
+    constexpr int LIST = NW * PARK;
+    constexpr int SUB = R < 32 ? R : 32;
+    constexpr int NSUB = R / SUB;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(PPC >= 1, "batch smaller than one probe");
+    __shared__ PoolShared<NR, DEBUG> sm;
+    __shared__ unsigned short sm_list[3][LIST];   // [0] = stragglers of pass 0, [1],[2] ping-pong afterwards
+    __shared__ short4 sm_req[PPC];
+    __shared__ int sm_next, sm_park[3], sm_chunk;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long wg0 = a.wg_begin + (long long)blockIdx.x * PPC;
+    const long long left = a.wg_end - wg0;
+    const int nprobes = left < PPC ? (int)left : PPC;
+    const int nrays = nprobes * R;
+    for (int i = tid; i < nprobes; i += THREADS) sm_req[i] = a.requests[(wg0 + i) * (long long)a.size + a.shift];
+    if (tid == 0) { sm_next = 0; sm_park[0] = 0; sm_park[1] = 0; sm_park[2] = 0; sm_chunk = 0; }
+    __syncthreads();
+
+    // ---- phase A: setup ----
+    for (int r = tid; r < nrays; r += THREADS) {
+        const int pr = r / R, ray = r % R;
+        const short4 rq = sm_req[pr];
+        const uint32_t gid_x = (uint32_t)((wg0 + pr) * R + ray);
+        const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
+        f3 o, d, inv;
+        setup_ray(rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, o, d, inv);
+        sm.o[0][r] = o.x; sm.o[1][r] = o.y; sm.o[2][r] = o.z;
+        sm.d[0][r] = d.x; sm.d[1][r] = d.y; sm.d[2][r] = d.z;
+        sm.inv[0][r] = inv.x; sm.inv[1][r] = inv.y; sm.inv[2][r] = inv.z;
+        sm.t[r] = 0.0f;
+        sm.done[r] = 0;
+        if constexpr (DEBUG) sm.ns[r] = 0;
+    }
+    __syncthreads();
+
+    // ---- phase B, pass 0: every warp marches ----
+    const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
+    pool_march<NR, PARK, DEBUG>(sm, s, mc, &sm_next, nullptr, nrays, sm_list[0], &sm_park[0], NW > 1, true, lane);
+    __syncthreads();
+    const int parked0 = sm_park[0];
+    const int tail_warps = parked0 == 0 ? 0 : max(1, min(NW, (parked0 + 47) / 48));
+    const int tail_threads = tail_warps * 32;
+
+    // ---- phase B': the tail warps march the stragglers among themselves ----
+    if (warp < tail_warps) {
+        int limit = parked0, rd = 0;                       // list index read in this pass
+        for (;;) {
+            const int wr = rd == 1 ? 2 : 1;
+            if (tid == 0) { sm_next = 0; sm_park[wr] = 0; }
+            asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
+            const int parts = max(1, min(tail_warps, (limit + 47) / 48));
+            if (warp < parts)
+                pool_march<NR, PARK, DEBUG>(sm, s, mc, &sm_next, sm_list[rd], limit, sm_list[wr], &sm_park[wr], parts > 1, false, lane);
+            asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
+            const int parked = sm_park[wr];
+            if (parked == 0) break;
+            limit = parked;
+            rd = wr;
+        }
+    }
+
+    // ---- phase C: refine + shade; 32 slots per claim ----
+    const f3 sun = {a.sun_x, a.sun_y, a.sun_z};
+    unsigned long long my_s = 0, my_h = 0;
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&sm_chunk, 32);
+        c = __shfl_sync(FULL, c, 0);
+        if (c >= nrays) break;
+        const int r = c + lane;
+        if (r < nrays && sm.done[r]) pool_shade<NR, R, DEBUG>(sm, s, a, wg0, r, sun, my_s, my_h);
+    }
+    if (warp < tail_warps)                                 // the stragglers, now finished too
+        for (int i = tid; i < parked0; i += tail_threads)
+            pool_shade<NR, R, DEBUG>(sm, s, a, wg0, sm_list[0][i], sun, my_s, my_h);
+    if constexpr (DEBUG) {
+#pragma unroll
+        for (int k = 16; k >= 1; k >>= 1) {
+            my_s += __shfl_xor_sync(FULL, my_s, k);
+            my_h += __shfl_xor_sync(FULL, my_h, k);
+        }
+        if (lane == 0) { atomicAdd(a.dbg_totals, my_s); atomicAdd(a.dbg_totals + 1, my_h); }
+    }
+    __syncthreads();
+
+    // ---- phase D: reduce + blend ----
+    for (int pr = warp; pr < nprobes; pr += NW) {
+        float fr = 0.0f, fg = 0.0f, fb = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NSUB; g++) {
+            const int r = pr * R + g * SUB + lane;
+            float lx = lane < SUB ? sm.o[0][r] : 0.0f, ly = lane < SUB ? sm.o[1][r] : 0.0f, lz = lane < SUB ? sm.o[2][r] : 0.0f;
+#pragma unroll
+            for (int k = SUB / 2; k >= 1; k >>= 1) {
+                lx += __shfl_xor_sync(FULL, lx, k);
+                ly += __shfl_xor_sync(FULL, ly, k);
+                lz += __shfl_xor_sync(FULL, lz, k);
+            }
+            fr += lx / (float)SUB; fg += ly / (float)SUB; fb += lz / (float)SUB;
+        }
+        fr /= (float)NSUB; fg /= (float)NSUB; fb /= (float)NSUB;
+        if (lane == 0) {
+            const long long w = wg0 + pr;
+            const short4 rq = sm_req[pr];
+            if constexpr (DEBUG) {
+                if (a.dbg_pre_blend) {
+                    a.dbg_pre_blend[3 * w] = fr; a.dbg_pre_blend[3 * w + 1] = fg; a.dbg_pre_blend[3 * w + 2] = fb;
+                }
+            }
+            uint32_t word = 0;
+            if ((unsigned)rq.x < (unsigned)s.wx && (unsigned)rq.y < (unsigned)s.wy && (unsigned)rq.z < (unsigned)s.wz) {
+                f3 old = unpack10(__ldg(s.field + (rq.x + s.wx * (rq.y + s.wy * rq.z))));
+                old.x = gmin(gmax(old.x, 0.0f), 1.0f); old.y = gmin(gmax(old.y, 0.0f), 1.0f); old.z = gmin(gmax(old.z, 0.0f), 1.0f);
+                const float t = a.reactiveness, omt = 1.0f - t;
+                word = pack10(old.x * omt + fr * t, old.y * omt + fg * t, old.z * omt + fb * t);
+            }
+            a.staged[w] = word;
+        }
+    }
+}
+
 // Deferred imageStore (radiance.comp:353): scatter the staged texels of workgroups
 // [wg_begin, wg_end) into the field once every read of the old field is done.
 __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__restrict__ staged,

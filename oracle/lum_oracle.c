@@ -305,6 +305,14 @@ int lum_oracle_update(const LumOracleScene *s, const uint32_t *field_old, uint32
                       const int16_t *req, int64_t nreq, int time_seed, int size, int shift,
                       float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
                       uint64_t totals[3], int nthreads) {
+    return lum_oracle_update_ex(s, field_old, field_new, req, nreq, time_seed, size, shift, pre_blend,
+                                ray_samples, ray_hits, NULL, totals, nthreads);
+}
+
+int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uint32_t *field_new,
+                         const int16_t *req, int64_t nreq, int time_seed, int size, int shift,
+                         float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, uint16_t *ray_coarse,
+                         uint64_t totals[3], int nthreads) {
     const int R = s->rays_per_probe;
     const int sub = R < 32 ? R : 32;                                     /* subgroup width used */
     const int nsub = R / sub;                                            /* SUBGROUSPS_PER_WORKGROUP :403 */
@@ -332,6 +340,7 @@ int lum_oracle_update(const LumOracleScene *s, const uint32_t *field_old, uint32
             S += ns; H += (uint64_t)ray.hit;
             if (ray_samples) ray_samples[w * R + i] = ns;
             if (ray_hits) ray_hits[w * R + i] = (uint8_t)ray.hit;
+            if (ray_coarse) ray_coarse[w * R + i] = (uint16_t)ray.coarse_samples;
         }
         float fr = 0.0f, fg = 0.0f, fb = 0.0f;                           /* :401 */
         for (int g = 0; g < nsub; g++) {                                 /* :386,398,404-406 */

@@ -91,6 +91,14 @@ int lum_oracle_update(const LumOracleScene *s, const uint32_t *field_old, uint32
                       float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
                       uint64_t totals[3], int nthreads);
 
+/* Same, with one more optional output: ray_coarse [nwg*R] = iterations of the coarse loop per ray
+ * (used to study warp scheduling policies offline). */
+int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uint32_t *field_new,
+                         const int16_t *requests_xyzw, int64_t nreq,
+                         int time_seed, int size, int shift,
+                         float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, uint16_t *ray_coarse,
+                         uint64_t totals[3], int nthreads);
+
 /* shift_radiance (internal_render.cpp:1218-1335): out[p] = in[p + shift] where p + shift is
  * inside the world, else unchanged in[p] (the reference copies only the overlapping box via a
  * temporary image).  |shift| >= world size on any axis is a no-op (the reference tests x only,

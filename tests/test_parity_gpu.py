@@ -20,28 +20,33 @@ def bits(a):
 
 
 def assert_update_equal(st, O, sc, f0, req, seed, size=1, shift=0, rays=True):
-    st.upload_field(f0)
+    """Both kernel variants (1 = pooled production kernel, 0 = one workgroup per CTA), instrumented
+    and plain, against the oracle: sample counts, hits, pre-blend radiance and field bit for bit."""
     st.set_requests(req)
-    st.set_debug(DEBUG_PRE_BLEND | (DEBUG_RAYS if rays else 0))
-    st.update(seed, size, shift)
     nwg = len(req) // size
-    dbg = st.download_debug(nwg, rays=rays)
-    got = st.download_field()
     ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=rays)
-    if rays:
-        assert np.array_equal(dbg["ray_samples"], ref["ray_samples"])
-        assert np.array_equal(dbg["ray_hits"], ref["ray_hits"])
-    assert dbg["totals"] == ref["totals"]
-    # -0.0 == +0.0 is allowed; everything else must match bit for bit
-    assert np.array_equal(dbg["pre_blend"], ref["pre_blend"])
-    nz = ref["pre_blend"] != 0
-    assert np.array_equal(bits(dbg["pre_blend"])[nz], bits(ref["pre_blend"])[nz])
-    assert np.array_equal(got, ref["field"])
-    # the non-instrumented kernel gives the same field
-    st.upload_field(f0)
-    st.set_debug(0)
-    st.update(seed, size, shift)
-    assert np.array_equal(st.download_field(), ref["field"])
+    for variant in (1, 0):
+        st.set_kernel_variant(variant)
+        st.upload_field(f0)
+        st.set_debug(DEBUG_PRE_BLEND | (DEBUG_RAYS if rays else 0))
+        st.update(seed, size, shift)
+        dbg = st.download_debug(nwg, rays=rays)
+        got = st.download_field()
+        if rays:
+            assert np.array_equal(dbg["ray_samples"], ref["ray_samples"]), variant
+            assert np.array_equal(dbg["ray_hits"], ref["ray_hits"]), variant
+        assert dbg["totals"] == ref["totals"], variant
+        # -0.0 == +0.0 is allowed; everything else must match bit for bit
+        assert np.array_equal(dbg["pre_blend"], ref["pre_blend"]), variant
+        nz = ref["pre_blend"] != 0
+        assert np.array_equal(bits(dbg["pre_blend"])[nz], bits(ref["pre_blend"])[nz]), variant
+        assert np.array_equal(got, ref["field"]), variant
+        # the non-instrumented kernel gives the same field
+        st.upload_field(f0)
+        st.set_debug(0)
+        st.update(seed, size, shift)
+        assert np.array_equal(st.download_field(), ref["field"]), variant
+    st.set_kernel_variant(1)
     return ref
 
 
