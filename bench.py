@@ -116,25 +116,21 @@ class ClockSampler:
         return out
 
 
-def cuda_iface(ptr, n):
-    class _A:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
-    return _A()
-
-
 # ----------------------------------------------------------------------------- ours -------
 class Runner:
     """One rank's stage + the per-step sequences (value region and e2e region)."""
 
     def __init__(self, scene, device, rank, world_size, torch, dist):
         import lum_b200
+        from lum_b200 import distributed as D
+        self.D = D
         self.torch, self.dist = torch, dist
         self.rank, self.n = rank, world_size
         self.scene = scene
         wz, wy, wx = scene["world"].shape
         if wz % world_size:
             raise SystemExit(f"world z={wz} not divisible by {world_size} ranks")
-        self.z0, self.z1 = wz // world_size * rank, wz // world_size * (rank + 1)
+        self.z0, self.z1 = D.slab_bounds(wz, rank, world_size)
         self.st = lum_b200.RadianceStage((wx, wy, wz), scene["bricks"].shape[0], rays_per_probe=RAYS, device=device)
         self.st.upload_world(scene["world"])
         self.st.upload_bricks(0, scene["bricks"])
@@ -143,7 +139,8 @@ class Runner:
         self.cells = wx * wy * wz
         self.slab_cells = self.cells // world_size
         self.stream = torch.cuda.ExternalStream(self.st.stream(), device=device)
-        self.field_t = torch.as_tensor(cuda_iface(self.st.field_device_ptr(), self.cells), device=f"cuda:{device}")
+        self.dims = (wx, wy, wz)
+        self.field_t = D.device_tensor_view(self.st.field_device_ptr(), self.cells, f"cuda:{device}")
         self.world_host = np.ascontiguousarray(scene["world"], np.int16)
         self.field_host = np.empty(self.cells, np.uint32)
         self.zero_field = np.zeros(self.cells, np.uint32)
@@ -160,8 +157,7 @@ class Runner:
     def exchange(self):
         if self.n > 1:
             with self.torch.cuda.stream(self.stream):
-                shard = self.field_t[self.rank * self.slab_cells:(self.rank + 1) * self.slab_cells]
-                self.dist.all_gather_into_tensor(self.field_t, shard)
+                self.D.all_gather_field(self.field_t, self.dims, self.rank, self.n)
 
     def step_resident(self, seed):
         if self.n > 1:

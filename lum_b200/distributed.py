@@ -1,0 +1,55 @@
+"""Multi-GPU plumbing of the radiance stage: probe sharding by z-slab + per-frame field exchange.
+
+Design: the read-only world / palette / materials are replicated on every
+rank; the field is replicated too and updated Jacobi-style.  Rank r of N owns the contiguous
+z-slab [r*Z/N, (r+1)*Z/N) of the field (the field is z-major, so a slab is one contiguous range of
+words), updates exactly the probes of that slab (lumcu_update_slab) and then all ranks exchange
+their slabs with ONE in-place all-gather, after which every rank holds the identical new field for
+the next frame's gathers.  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
+CPU for the tests of this host-side logic).
+"""
+from __future__ import annotations
+
+
+def slab_bounds(wz: int, rank: int, world_size: int):
+    """z range [z0, z1) owned by `rank`.  Requires wz % world_size == 0 (16 and 64 both divide by 8)."""
+    if wz % world_size:
+        raise ValueError(f"world z extent {wz} is not divisible by {world_size} ranks")
+    h = wz // world_size
+    return rank * h, (rank + 1) * h
+
+
+def slab_words(dims, rank: int, world_size: int):
+    """[begin, end) of the rank's slab in field words (field index = x + X*(y + Y*z))."""
+    wx, wy, wz = dims
+    z0, z1 = slab_bounds(wz, rank, world_size)
+    return wx * wy * z0, wx * wy * z1
+
+
+def all_gather_field(field, dims, rank: int, world_size: int, group=None):
+    """In-place all-gather of the ranks' z-slabs of `field` (a flat 1-D torch tensor of the whole
+    field, on CPU for gloo or on the GPU for NCCL).  The send buffer is the rank's own slab inside
+    the receive buffer, the layout ncclAllGather accepts in place."""
+    import torch.distributed as dist
+    if world_size == 1:
+        return field
+    b, e = slab_words(dims, rank, world_size)
+    shard = field[b:e]
+    if field.is_cuda:
+        dist.all_gather_into_tensor(field, shard, group=group)
+    else:  # gloo has no all_gather_into_tensor on every build: gather views of the same storage
+        n = e - b
+        outs = [field[i * n:(i + 1) * n] for i in range(world_size)]
+        dist.all_gather(outs, shard.clone(), group=group)
+    return field
+
+
+def device_tensor_view(ptr: int, nwords: int, device):
+    """A torch int32 tensor aliasing `nwords` 32-bit words of device memory at `ptr` (the field
+    buffer owned by the stage), so NCCL can exchange it without a copy."""
+    import torch
+
+    class _Iface:
+        __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Iface(), device=device)

@@ -49,6 +49,7 @@ def lib():
         _lib = C.CDLL(_LIB_PATH)
         _lib.lum_oracle_build_requests.restype = C.c_int64
         _lib.lum_oracle_update.restype = C.c_int
+        _lib.lum_oracle_update_ex.restype = C.c_int
         _lib.lum_oracle_pack_rgb10a2.restype = C.c_uint32
         _lib.lum_oracle_max_threads.restype = C.c_int
     return _lib
@@ -146,7 +147,7 @@ def trace(scene: Scene, field, probe, gid_x, ray_index, time_seed, table=None):
 
 
 def update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, nthreads=0,
-           want_rays=False):
+           want_rays=False, wg_range=None):
     """Returns dict(field, pre_blend, totals=(S,H,N), threads[, ray_samples, ray_hits])."""
     field_old = np.ascontiguousarray(field_old, np.uint32).reshape(-1)
     assert field_old.size == scene.cells
@@ -158,9 +159,11 @@ def update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, nthrea
     rs = np.zeros(nwg * scene.rays, np.uint32) if want_rays else None
     rh = np.zeros(nwg * scene.rays, np.uint8) if want_rays else None
     tot = (C.c_uint64 * 3)()
-    used = lib().lum_oracle_update(C.byref(scene.c), _p(field_old), _p(field_new), _p(req),
-                                   C.c_int64(nreq), C.c_int(time_seed), C.c_int(size), C.c_int(shift),
-                                   _p(pre), _p(rs), _p(rh), tot, C.c_int(nthreads))
+    b, e = (0, -1) if wg_range is None else wg_range
+    used = lib().lum_oracle_update_ex(C.byref(scene.c), _p(field_old), _p(field_new), _p(req),
+                                      C.c_int64(nreq), C.c_int(time_seed), C.c_int(size), C.c_int(shift),
+                                      _p(pre), _p(rs), _p(rh), None, tot, C.c_int(nthreads),
+                                      C.c_int64(b), C.c_int64(e))
     res = dict(field=field_new, pre_blend=pre, totals=(int(tot[0]), int(tot[1]), int(tot[2])),
                threads=used)
     if want_rays:

@@ -306,17 +306,19 @@ int lum_oracle_update(const LumOracleScene *s, const uint32_t *field_old, uint32
                       float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
                       uint64_t totals[3], int nthreads) {
     return lum_oracle_update_ex(s, field_old, field_new, req, nreq, time_seed, size, shift, pre_blend,
-                                ray_samples, ray_hits, NULL, totals, nthreads);
+                                ray_samples, ray_hits, NULL, totals, nthreads, 0, -1);
 }
 
 int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uint32_t *field_new,
                          const int16_t *req, int64_t nreq, int time_seed, int size, int shift,
                          float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, uint16_t *ray_coarse,
-                         uint64_t totals[3], int nthreads) {
+                         uint64_t totals[3], int nthreads, int64_t wg_begin, int64_t wg_end) {
     const int R = s->rays_per_probe;
     const int sub = R < 32 ? R : 32;                                     /* subgroup width used */
     const int nsub = R / sub;                                            /* SUBGROUSPS_PER_WORKGROUP :403 */
     const int64_t nwg = (size > 0) ? nreq / size : 0;                    /* internal_render.cpp:1204 */
+    if (wg_end < 0 || wg_end > nwg) wg_end = nwg;                        /* optional sub-range of the dispatch */
+    if (wg_begin < 0) wg_begin = 0;
     size_t cells = (size_t)s->wx * (size_t)s->wy * (size_t)s->wz;
     if (field_new != field_old) memcpy(field_new, field_old, cells * sizeof(uint32_t));
     float *table = (float *)malloc(sizeof(float) * 3 * (size_t)R);
@@ -328,7 +330,7 @@ int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uin
     used = nthreads;
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(+ : S, H)
 #endif
-    for (int64_t w = 0; w < nwg; w++) {
+    for (int64_t w = wg_begin; w < wg_end; w++) {
         int64_t rq = w * (int64_t)size + shift;                          /* :368 */
         const int16_t *p = req + 4 * rq;                                 /* :369 */
         float lr[256], lg[256], lb[256];
@@ -361,7 +363,7 @@ int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uin
         }
     }
     free(table);
-    if (totals) { totals[0] = S; totals[1] = H; totals[2] = (uint64_t)nwg; }
+    if (totals) { totals[0] = S; totals[1] = H; totals[2] = (uint64_t)(wg_end > wg_begin ? wg_end - wg_begin : 0); }
     return used;
 }
 

@@ -91,13 +91,16 @@ int lum_oracle_update(const LumOracleScene *s, const uint32_t *field_old, uint32
                       float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
                       uint64_t totals[3], int nthreads);
 
-/* Same, with one more optional output: ray_coarse [nwg*R] = iterations of the coarse loop per ray
- * (used to study warp scheduling policies offline). */
+/* Same, with one more optional output, ray_coarse [nwg*R] = iterations of the coarse loop per ray
+ * (used to study warp scheduling policies offline), and an optional sub-range [wg_begin, wg_end)
+ * of the dispatch's workgroups (wg_end < 0 = all): only those probes are updated, with their
+ * global workgroup indices (what one rank of a probe-sharded update computes).  Output arrays
+ * stay indexed by the global workgroup index. */
 int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uint32_t *field_new,
                          const int16_t *requests_xyzw, int64_t nreq,
                          int time_seed, int size, int shift,
                          float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, uint16_t *ray_coarse,
-                         uint64_t totals[3], int nthreads);
+                         uint64_t totals[3], int nthreads, int64_t wg_begin, int64_t wg_end);
 
 /* shift_radiance (internal_render.cpp:1218-1335): out[p] = in[p + shift] where p + shift is
  * inside the world, else unchanged in[p] (the reference copies only the overlapping box via a

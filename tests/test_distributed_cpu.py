@@ -1,0 +1,82 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: z-slab sharding + in-place field
+all-gather reproduce the single-rank update.  The per-rank compute is the oracle here (test
+infrastructure standing in for lumcu_update_slab, which needs a GPU); the sharding arithmetic and
+the exchange are the product code under test (lum_b200/distributed.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lum_b200 import distributed as D
+from lum_b200 import scenes
+
+
+def test_slab_arithmetic():
+    assert D.slab_bounds(16, 0, 8) == (0, 2) and D.slab_bounds(16, 7, 8) == (14, 16)
+    assert D.slab_words((48, 48, 16), 1, 2) == (48 * 48 * 8, 48 * 48 * 16)
+    with pytest.raises(ValueError):
+        D.slab_bounds(16, 0, 3)
+    cover = []
+    for r in range(4):
+        cover += list(range(*D.slab_bounds(64, r, 4)))
+    assert cover == list(range(64))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, frames, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    d = scenes.demo_scene()
+    sc = O.Scene(d["world"], d["bricks"], d["materials"])
+    dims = (sc.wx, sc.wy, sc.wz)
+    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16)      # unsorted special tail
+    req = O.build_requests(d["world"], sp)
+    z0, z1 = D.slab_bounds(sc.wz, rank, world)
+    mine = np.nonzero((req[:, 2] >= z0) & (req[:, 2] < z1))[0]                   # this rank's workgroups
+    field = torch.zeros(sc.cells, dtype=torch.int32)
+    for f in range(frames):
+        old = field.numpy().view(np.uint32).copy()
+        new = old.copy()
+        # contiguous runs of this rank's workgroup indices, computed with their GLOBAL indices
+        runs = np.split(mine, np.nonzero(np.diff(mine) != 1)[0] + 1) if len(mine) else []
+        for run in runs:
+            r = O.update(sc, old, req, f, wg_range=(int(run[0]), int(run[-1]) + 1), nthreads=2)
+            ch = r["field"] != old
+            new[ch] = r["field"][ch]
+        field = torch.from_numpy(new.view(np.int32).copy())
+        D.all_gather_field(field, dims, rank, world)
+    np.save(os.path.join(out_dir, f"field_{rank}.npy"), field.numpy().view(np.uint32))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_matches_single_rank(tmp_path):
+    import oracle as O
+    frames = 3
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, frames, str(tmp_path)), nprocs=2, join=True)
+    d = scenes.demo_scene()
+    sc = O.Scene(d["world"], d["bricks"], d["materials"])
+    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16)
+    req = O.build_requests(d["world"], sp)
+    f = np.zeros(sc.cells, np.uint32)
+    for k in range(frames):
+        f = O.update(sc, f, req, k)["field"]
+    a = np.load(tmp_path / "field_0.npy")
+    b = np.load(tmp_path / "field_1.npy")
+    assert np.array_equal(a, b)          # every rank ends with the identical field
+    assert np.array_equal(a, f)          # and it is the single-rank result

@@ -1,0 +1,66 @@
+"""2-GPU test (skipped on a 1-GPU box): z-slab sharded update + NCCL all-gather through
+torch.distributed equals the single-GPU update, bit for bit."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["LUM_ROOT"])
+import lum_b200
+from lum_b200 import scenes, distributed as D
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{rank}"))
+sc = scenes.synthetic_scene(64, 48, 16, palette=64, seed=5)
+wz, wy, wx = sc["world"].shape
+st = lum_b200.RadianceStage((wx, wy, wz), 64, device=rank)
+st.upload_world(sc["world"]); st.upload_bricks(0, sc["bricks"]); st.upload_materials(sc["materials"])
+sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16)
+st.build_requests(sp)
+field = D.device_tensor_view(st.field_device_ptr(), st.cells, f"cuda:{rank}")
+stream = torch.cuda.ExternalStream(st.stream(), device=rank)
+z0, z1 = D.slab_bounds(wz, rank, world)
+for f in range(4):
+    st.update_slab(f, 1, 0, z0, z1)
+    with torch.cuda.stream(stream):
+        D.all_gather_field(field, (wx, wy, wz), rank, world)
+out = st.download_field()
+np.save(os.path.join(os.environ["OUT_DIR"], f"f{rank}.npy"), out)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_slabs_match_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import lum_b200
+    from lum_b200 import scenes
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    env = dict(os.environ, LUM_ROOT=ROOT, OUT_DIR=str(tmp_path))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                    "--master-addr", "127.0.0.1", "--master-port", str(port), str(w)],
+                   check=True, env=env, timeout=600)
+    sc = scenes.synthetic_scene(64, 48, 16, palette=64, seed=5)
+    st = lum_b200.RadianceStage((64, 48, 16), 64)
+    st.upload_world(sc["world"]); st.upload_bricks(0, sc["bricks"]); st.upload_materials(sc["materials"])
+    st.build_requests(np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16))
+    for f in range(4):
+        st.update(f)
+    ref = st.download_field()
+    a, b = np.load(tmp_path / "f0.npy"), np.load(tmp_path / "f1.npy")
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, ref)
