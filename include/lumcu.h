@@ -110,6 +110,36 @@ int lumcu_update_slab(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t sh
 /* shift_radiance (internal_render.cpp:1218-1335): field[p] = field[p + d] over the overlap box. */
 int lumcu_shift(LumcuCtx *ctx, int32_t dx, int32_t dy, int32_t dz);
 
+/* ---- feeders of the pass: blockify copies + map.comp -------------------- */
+
+/* create_RayTrace_VoxelImages of load_mesh (load_stuff.cpp:376-385): device copy of a model's voxel
+ * grid, voxels[x + sx*(y + sy*z)] (the .vox order, load_stuff.cpp:296).  *out_model is a handle >= 0. */
+int lumcu_upload_model(LumcuCtx *ctx, const uint8_t *voxels, int32_t sx, int32_t sy, int32_t sz, int32_t *out_model);
+/* free_mesh (load_stuff.cpp:397-430), voxel image part. */
+int lumcu_free_model(LumcuCtx *ctx, int32_t model);
+
+/* The brick part of exec_copies (internal_render.cpp:1402-1446) for the blocks blockify_mesh allocated
+ * (:1029-1076): for i in [0,n): bricks[dst_ids[i]] = src_ids[i] == 0 ? all-zero : bricks[src_ids[i]].
+ * Device-to-device: no brick data crosses PCIe per frame.  (The reference clears the whole atlas and
+ * re-copies the static bricks; here the static bricks are never overwritten, and every dynamic brick
+ * the world references is rewritten by this call, so the visible state is the same.) */
+int lumcu_copy_bricks(LumcuCtx *ctx, const int32_t *src_ids, const int32_t *dst_ids, int32_t n);
+
+/* map_mesh + shaders/map.comp (internal_render.cpp:1485-1527, map.comp:32-67): for every world voxel
+ * g in [0, 4*ceil(area/4)) (the dispatch's invocations) at world position (g + 0.5 + shift), fetch the
+ * model voxel at trunc(inverse_trans * (pos,1)) and, if it is non-zero and the world block under pos
+ * is dynamic (id >= static_block_count; map.comp:28 hard-codes 15), store it into that block's brick.
+ * inverse_trans: 16 floats, column-major (glm mat4 memory order), = mat4(inverse(shift*rotate));
+ * shift = floor(aabb.min), area = ceil(aabb.max) - floor(aabb.min) (internal_render.cpp:1506-1512).
+ * Models mapped by successive calls are applied in call order (the reference records the dispatches
+ * without barriers between them; overlapping models race there, here the later one wins). */
+int lumcu_map_model(LumcuCtx *ctx, int32_t model, const float inverse_trans[16], const int32_t shift[3],
+                    const int32_t area[3], int32_t static_block_count);
+
+/* Readbacks for tests / host-side consumers. */
+int lumcu_download_bricks(LumcuCtx *ctx, int32_t first_id, int32_t count, uint8_t *voxels);
+int lumcu_download_world(LumcuCtx *ctx, int16_t *world_xyz);
+
 /* Field snapshots (the reference never reads the image back; needed by tests and by any
  * host-side consumer).  field_xyz: world cells uint32. */
 int lumcu_upload_field(LumcuCtx *ctx, const uint32_t *field_xyz);

@@ -50,6 +50,12 @@ SYMBOLS = {
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lumcu_update_slab": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "lumcu_shift": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_upload_model": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+    "lumcu_free_model": (C.c_int, [_P, C.c_int32]),
+    "lumcu_copy_bricks": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "lumcu_map_model": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int32]),
+    "lumcu_download_bricks": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "lumcu_download_world": (C.c_int, [_P, _P]),
     "lumcu_upload_field": (C.c_int, [_P, _P]),
     "lumcu_download_field": (C.c_int, [_P, _P]),
     "lumcu_direction_table": (C.c_int, [_P, _P]),
@@ -169,6 +175,39 @@ class RadianceStage:
 
     def shift(self, dx, dy, dz):
         self._ck(self.lib.lumcu_shift(self.ctx, int(dx), int(dy), int(dz)))
+
+    # -- feeders: blockify copies + map.comp ------------------------------------------------
+    def upload_model(self, voxels_zyx):
+        v = np.ascontiguousarray(voxels_zyx, np.uint8)
+        sz, sy, sx = v.shape
+        h = C.c_int32()
+        self._ck(self.lib.lumcu_upload_model(self.ctx, _ptr(v), sx, sy, sz, C.byref(h)))
+        return h.value
+
+    def free_model(self, model):
+        self._ck(self.lib.lumcu_free_model(self.ctx, int(model)))
+
+    def copy_bricks(self, src_ids, dst_ids):
+        s = np.ascontiguousarray(src_ids, np.int32)
+        d = np.ascontiguousarray(dst_ids, np.int32)
+        assert s.shape == d.shape
+        self._ck(self.lib.lumcu_copy_bricks(self.ctx, _ptr(s), _ptr(d), s.size))
+
+    def map_model(self, model, inverse_trans, shift, area, static_block_count):
+        m = np.ascontiguousarray(inverse_trans, np.float32).reshape(16)
+        sh = np.ascontiguousarray(shift, np.int32).reshape(3)
+        ar = np.ascontiguousarray(area, np.int32).reshape(3)
+        self._ck(self.lib.lumcu_map_model(self.ctx, int(model), _ptr(m), _ptr(sh), _ptr(ar), int(static_block_count)))
+
+    def download_bricks(self, first, count):
+        out = np.empty((count, 16, 16, 16), np.uint8)
+        self._ck(self.lib.lumcu_download_bricks(self.ctx, int(first), int(count), _ptr(out)))
+        return out
+
+    def download_world(self):
+        out = np.empty((self.wz, self.wy, self.wx), np.int16)
+        self._ck(self.lib.lumcu_download_world(self.ctx, _ptr(out)))
+        return out
 
     # -- readbacks ------------------------------------------------------------------------
     def request_count(self):

@@ -24,10 +24,18 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,
           "-I", os.path.join(ROOT, "include")]
 
 TARGETS = {
+    # the CUDA stage: kernels + C-ABI (include/lumcu.h)
     "liblumcu.so": dict(
         sources=["lumcu.cu"],
         deps=["radiance_device.cuh", "radiance_kernels.cuh", "../../include/lumcu.h"],
         extra=[]),
+    # host side above the C-ABI: Lum::Renderer / lum_* mirror (include/lum.hpp, include/clum.h).  Plain C++,
+    # built with nvcc as the driver only so one toolchain call covers everything; links liblumcu.so.
+    "liblum.so": dict(
+        sources=["host/lum_internal.cpp", "host/lum_renderer.cpp", "host/lum_c_api.cpp", "host/vox.cpp"],
+        deps=["host/host_math.hpp", "host/vox.hpp", "../../include/lum.hpp", "../../include/lum_opaque.hpp",
+              "../../include/lum_math.hpp", "../../include/clum.h", "../../include/lumcu.h", "../liblumcu.so"],
+        extra=["-L", HERE, "-llumcu", "-Xlinker", "-rpath,$ORIGIN"]),
 }
 
 

@@ -122,7 +122,13 @@ struct LumcuCtx {
     long long dbg_nwg = 0;       // workgroups of the last instrumented update
     long long dbg_wg_begin = 0;
 
-    Staging stage_world, stage_req, stage_misc;
+    // models (map.comp inputs) and blockify copy pairs
+    struct Model { uint8_t *d_vox = nullptr; int sx = 0, sy = 0, sz = 0; };
+    std::vector<Model> models;
+    int2 *d_pairs = nullptr;
+    long long pairs_cap = 0;
+
+    Staging stage_world, stage_req, stage_misc, stage_pairs;
     uint64_t launches = 0;
 };
 
@@ -333,9 +339,10 @@ int lumcu_destroy(LumcuCtx *c) {
     cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_field);
     cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
     cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
-    cudaFree(c->d_special); cudaFree(c->d_bounds);
+    cudaFree(c->d_special); cudaFree(c->d_bounds); cudaFree(c->d_pairs);
+    for (auto &m : c->models) cudaFree(m.d_vox);
     cudaFree(c->d_pre_blend); cudaFree(c->d_ray_samples); cudaFree(c->d_ray_hits); cudaFree(c->d_totals);
-    c->stage_world.release(); c->stage_req.release(); c->stage_misc.release();
+    c->stage_world.release(); c->stage_req.release(); c->stage_misc.release(); c->stage_pairs.release();
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
@@ -383,6 +390,104 @@ int lumcu_upload_materials(LumcuCtx *c, const float *m) {
     if (!m) return fail(LUMCU_E_ARG, "null materials");
     if (int rc = staged_upload(c, c->stage_misc, c->d_materials, m, 256 * 6 * sizeof(float))) return rc;
     c->have_materials = true;
+    return 0;
+}
+
+
+int lumcu_upload_model(LumcuCtx *c, const uint8_t *vox, int32_t sx, int32_t sy, int32_t sz, int32_t *out) {
+    if (int rc = use(c)) return rc;
+    if (!vox || !out || sx < 1 || sy < 1 || sz < 1 || (long long)sx * sy * sz > (1ll << 30))
+        return fail(LUMCU_E_ARG, "bad model (%d x %d x %d)", sx, sy, sz);
+    const size_t bytes = (size_t)sx * sy * sz;
+    LumcuCtx::Model m;
+    CU(cudaMalloc(&m.d_vox, bytes));
+    m.sx = sx; m.sy = sy; m.sz = sz;
+    if (int rc = staged_upload(c, c->stage_misc, m.d_vox, vox, bytes)) { cudaFree(m.d_vox); return rc; }
+    int slot = -1;
+    for (size_t i = 0; i < c->models.size(); i++) if (!c->models[i].d_vox) { slot = (int)i; break; }
+    if (slot < 0) { c->models.push_back(m); slot = (int)c->models.size() - 1; } else c->models[slot] = m;
+    *out = slot;
+    return 0;
+}
+
+int lumcu_free_model(LumcuCtx *c, int32_t model) {
+    if (int rc = use(c)) return rc;
+    if (model < 0 || model >= (int)c->models.size() || !c->models[model].d_vox) return fail(LUMCU_E_ARG, "unknown model %d", model);
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->models[model].d_vox);
+    c->models[model] = LumcuCtx::Model();
+    return 0;
+}
+
+int lumcu_copy_bricks(LumcuCtx *c, const int32_t *src, const int32_t *dst, int32_t n) {
+    if (int rc = use(c)) return rc;
+    if (n < 0 || (n > 0 && (!src || !dst))) return fail(LUMCU_E_ARG, "bad brick copy list");
+    if (n == 0) return 0;
+    for (int i = 0; i < n; i++)
+        if (src[i] < 0 || src[i] >= c->desc.palette_capacity || dst[i] < 0 || dst[i] >= c->desc.palette_capacity)
+            return fail(LUMCU_E_ARG, "brick copy %d: %d -> %d outside palette capacity %d", i, src[i], dst[i], c->desc.palette_capacity);
+    if (c->pairs_cap < n) {
+        cudaFree(c->d_pairs); c->d_pairs = nullptr; c->pairs_cap = 0;
+        long long cap = std::max<long long>(n, 256);
+        CU(cudaMalloc(&c->d_pairs, (size_t)cap * sizeof(int2)));
+        c->pairs_cap = cap;
+    }
+    void *h; int slot;
+    if (int rc = c->stage_pairs.acquire((size_t)n * sizeof(int2), &h, &slot)) return rc;
+    int2 *hp = (int2 *)h;
+    for (int i = 0; i < n; i++) { hp[i].x = src[i]; hp[i].y = dst[i]; if (dst[i] == 0) c->brick0_empty = false; }
+    CU(cudaMemcpyAsync(c->d_pairs, hp, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->stage_pairs.done[slot], c->stream));
+    copy_bricks_kernel<<<(unsigned)n, 256, 0, c->stream>>>(c->d_bricks, c->d_pairs, n, c->desc.palette_capacity);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->have_bricks = true;
+    return 0;
+}
+
+int lumcu_map_model(LumcuCtx *c, int32_t model, const float inv[16], const int32_t shift[3], const int32_t area[3], int32_t static_count) {
+    if (int rc = use(c)) return rc;
+    if (model < 0 || model >= (int)c->models.size() || !c->models[model].d_vox) return fail(LUMCU_E_ARG, "unknown model %d", model);
+    if (!inv || !shift || !area) return fail(LUMCU_E_ARG, "null argument");
+    if (!c->have_world) return fail(LUMCU_E_STATE, "lumcu_map_model before lumcu_upload_world");
+    MapArgs a;
+    for (int i = 0; i < 16; i++) a.m[i] = inv[i];
+    long long total = 1;
+    for (int k = 0; k < 3; k++) {
+        a.shift[k] = shift[k];
+        // vkCmdDispatch((area+3)/4) with a negative or zero area dispatches nothing (internal_render.cpp:1517)
+        const int groups = (area[k] + 3) / 4;
+        a.ext[k] = groups > 0 ? groups * 4 : 0;
+        total *= a.ext[k];
+    }
+    if (total > (1ll << 40)) return fail(LUMCU_E_ARG, "map area too large");
+    if (static_count <= 0) c->brick0_empty = false;    // brick 0 becomes a store target (map.comp:62 with a zero threshold)
+    a.static_count = static_count;
+    const LumcuCtx::Model &m = c->models[model];
+    a.msx = m.sx; a.msy = m.sy; a.msz = m.sz;
+    if (total > 0) {
+        const int t = 256;
+        map_model_kernel<<<(unsigned)((total + t - 1) / t), t, 0, c->stream>>>(c->d_world, c->d_bricks, m.d_vox, c->wx, c->wy, c->wz, c->desc.palette_capacity, a);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+int lumcu_download_bricks(LumcuCtx *c, int32_t first, int32_t count, uint8_t *vox) {
+    if (int rc = use(c)) return rc;
+    if (!vox || count < 0 || first < 0 || first + count > c->desc.palette_capacity)
+        return fail(LUMCU_E_ARG, "brick range [%d,%d) outside palette capacity %d", first, first + count, c->desc.palette_capacity);
+    if (count > 0) CU(cudaMemcpyAsync(vox, c->d_bricks + (size_t)first * 4096, (size_t)count * 4096, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lumcu_download_world(LumcuCtx *c, int16_t *world) {
+    if (int rc = use(c)) return rc;
+    if (!world) return fail(LUMCU_E_ARG, "null world");
+    CU(cudaMemcpyAsync(world, c->d_world, (size_t)c->cells * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -22,7 +22,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "lum_oracle.c")
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("lum_oracle.c", "lum_oracle.h", "Makefile"))
+        for f in ("lum_oracle.c", "lum_oracle_feeders.c", "lum_oracle.h", "Makefile"))
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
     assert os.path.exists(src)
@@ -52,6 +52,7 @@ def lib():
         _lib.lum_oracle_update_ex.restype = C.c_int
         _lib.lum_oracle_pack_rgb10a2.restype = C.c_uint32
         _lib.lum_oracle_max_threads.restype = C.c_int
+        _lib.lum_oracle_blockify.restype = C.c_int32
     return _lib
 
 
@@ -183,3 +184,56 @@ def shift_field(field, dims, dx, dy, dz):
 
 def max_threads():
     return int(lib().lum_oracle_max_threads())
+
+
+# ---- feeders (lum_oracle_feeders.c) ---------------------------------------------------------
+class Placement(C.Structure):
+    _fields_ = [("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3),
+                ("block_min", C.c_int32 * 3), ("block_max", C.c_int32 * 3),
+                ("map_shift", C.c_int32 * 3), ("map_area", C.c_int32 * 3),
+                ("inverse_trans", C.c_float * 16)]
+
+
+def place_model(rot_wxyz, shift, size, world_size):
+    """rot (w,x,y,z), shift (voxels), size (sx,sy,sz), world_size (blocks) -> Placement."""
+    r = (C.c_float * 4)(*[float(v) for v in rot_wxyz])
+    s = (C.c_float * 3)(*[float(v) for v in shift])
+    z = (C.c_int32 * 3)(*[int(v) for v in size])
+    w = (C.c_int32 * 3)(*[int(v) for v in world_size])
+    out = Placement()
+    lib().lum_oracle_place_model(r, s, z, w, C.byref(out))
+    return out
+
+
+def blockify(origin_world, static_count, placements):
+    """-> (current_world, copy_src, copy_dst): start_blockify + blockify_mesh in draw order."""
+    ow = np.ascontiguousarray(origin_world, np.int16)
+    wz, wy, wx = ow.shape
+    cur = np.empty_like(ow)
+    arr = (Placement * max(1, len(placements)))(*placements)
+    cap = ow.size
+    src = np.zeros(cap, np.int32)
+    dst = np.zeros(cap, np.int32)
+    n = lib().lum_oracle_blockify(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(ow), _p(cur), C.c_int(static_count),
+                                  arr, C.c_int(len(placements)), _p(src), _p(dst), C.c_int32(cap))
+    return cur, src[:n].copy(), dst[:n].copy()
+
+
+def copy_bricks(bricks, src, dst):
+    """In place on `bricks` (uint8 [P,16,16,16], C-contiguous)."""
+    assert bricks.flags.c_contiguous and bricks.dtype == np.uint8
+    s = np.ascontiguousarray(src, np.int32)
+    d = np.ascontiguousarray(dst, np.int32)
+    lib().lum_oracle_copy_bricks(_p(bricks), C.c_int(bricks.shape[0]), _p(s), _p(d), C.c_int32(len(s)))
+
+
+def map_model(world, bricks, model, placement, static_count):
+    """map.comp for one model; `bricks` modified in place.  model: uint8 [sz,sy,sx] (x fastest)."""
+    w = np.ascontiguousarray(world, np.int16)
+    wz, wy, wx = w.shape
+    m = np.ascontiguousarray(model, np.uint8)
+    sz, sy, sx = m.shape
+    assert bricks.flags.c_contiguous and bricks.dtype == np.uint8
+    lib().lum_oracle_map_model(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(w), _p(bricks), C.c_int(bricks.shape[0]),
+                               _p(m), C.c_int(sx), C.c_int(sy), C.c_int(sz), placement.inverse_trans,
+                               placement.map_shift, placement.map_area, C.c_int(static_count))

@@ -109,6 +109,35 @@ int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uin
 void lum_oracle_shift_field(int wx, int wy, int wz, const uint32_t *in, uint32_t *out,
                             int dx, int dy, int dz);
 
+/* ---- feeders of the pass (lum_oracle_feeders.c) ------------------------------------------------ */
+
+/* What blockify_mesh and map_mesh derive from a MeshTransform + model size
+ * (internal_render.cpp:989-1016,1031-1041,1499-1513). */
+typedef struct {
+    float aabb_min[3], aabb_max[3];     /* get_shift: transformed AABB of box = size-1 (float)          */
+    int32_t block_min[3], block_max[3]; /* blockify border in blocks, clamped to the world              */
+    int32_t map_shift[3], map_area[3];  /* map_mesh: floor(min), ceil(max) - floor(min)                 */
+    float inverse_trans[16];            /* mat4(inverse(shift*rotate)), column-major                    */
+} LumOraclePlacement;
+
+/* rot = (w,x,y,z) as the C API passes it (crenderer.cpp:139-145). */
+void lum_oracle_place_model(const float rot_wxyz[4], const float shift[3], const int32_t size[3],
+                            const int32_t world_size[3], LumOraclePlacement *out);
+
+/* start_blockify + blockify_mesh per model in draw order (internal_render.cpp:977-987,1029-1076). */
+int32_t lum_oracle_blockify(int wx, int wy, int wz, const int16_t *origin_world, int16_t *current_world,
+                            int static_count, const LumOraclePlacement *models, int nmodels,
+                            int32_t *copy_src, int32_t *copy_dst, int32_t copy_cap);
+
+/* Per-block brick copies of exec_copies (internal_render.cpp:1402-1446); src 0 = zero the brick. */
+void lum_oracle_copy_bricks(uint8_t *bricks, int capacity, const int32_t *src, const int32_t *dst, int32_t n);
+
+/* shaders/map.comp:32-67 for one map_mesh dispatch (internal_render.cpp:1485-1518). */
+void lum_oracle_map_model(int wx, int wy, int wz, const int16_t *world, uint8_t *bricks, int capacity,
+                          const uint8_t *model, int sx, int sy, int sz,
+                          const float inverse_trans[16], const int32_t shift[3], const int32_t area[3],
+                          int static_count);
+
 int lum_oracle_max_threads(void);
 
 #ifdef __cplusplus
