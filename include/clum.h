@@ -49,54 +49,58 @@ typedef struct LumMeshTransform {
 } LumMeshTransform;
 #define LUM_DEFAULT_MESH_TRANSFORM ((LumMeshTransform){{1,0,0,0}, {0,0,0}})
 
+/* -- instance life cycle (crenderer.cpp:12-21, 30-45, 168-171) -- */
 LumRenderer lum_create_instance(const LumSettings* settings);
+void lum_init(LumRenderer instance, const LumSettings* settings);
+void lum_wait_idle(LumRenderer instance);
+void lum_cleanup(LumRenderer instance);                       /* also destroys the instance */
 void lum_destroy_instance(LumRenderer instance);
 
+/* -- world grid of block ids, x fastest (crenderer.cpp:23-27, 47-62) -- */
 void lum_demo_load_scene(LumRenderer instance, const char* path);
-
-void lum_init(LumRenderer instance, const LumSettings* settings);
-void lum_load_world(LumRenderer instance, const LumMeshBlock* world_data);
 void lum_load_world_file(LumRenderer instance, const char* file);
-
-void lum_set_world_block(LumRenderer instance, int x, int y, int z, LumMeshBlock block);
+void lum_load_world(LumRenderer instance, const LumMeshBlock* world_data);
 LumMeshBlock lum_get_world_block(const LumRenderer instance, int x, int y, int z);
+void lum_set_world_block(LumRenderer instance, int x, int y, int z, LumMeshBlock block);
 
-void lum_load_block(LumRenderer instance, LumMeshBlock block, void* block_data);
+/* -- block palette (16^3 voxel bricks, BlockVoxels[x][y][z]) and material palette (crenderer.cpp:64-80) -- */
 void lum_load_block_file(LumRenderer instance, LumMeshBlock block, const char* file);
-
+void lum_load_block(LumRenderer instance, LumMeshBlock block, void* block_data);
 void lum_upload_block_palette_to_gpu(LumRenderer instance);
 void lum_upload_material_palette_to_gpu(LumRenderer instance);
 
-LumMeshModel lum_load_mesh_file(LumRenderer instance, const char* file, bool try_extract_palette);
+/* -- voxel models; the first model loaded with try_extract_palette defines the materials (crenderer.cpp:82-99) -- */
 LumMeshModel lum_load_mesh_data(LumRenderer instance, void* mesh_data, int x_size, int y_size, int z_size);
+LumMeshModel lum_load_mesh_file(LumRenderer instance, const char* file, bool try_extract_palette);
 void lum_free_mesh(LumRenderer instance, LumMeshModel model);
 
-LumMeshFoliage lum_load_foliage(LumRenderer instance, const char* vertex_shader_file, int vertices_per_foliage, int density);
-LumMeshVolumetric lum_load_volumetric(LumRenderer instance, float max_density, float density_deviation, const uint8_t color[3]);
+/* -- raster-side resources: accepted, recorded, never drawn here (crenderer.cpp:101-121) -- */
 LumMeshLiquid lum_load_liquid(LumRenderer instance, int main_mat, int foam_mat);
+LumMeshVolumetric lum_load_volumetric(LumRenderer instance, float max_density, float density_deviation, const uint8_t color[3]);
+LumMeshFoliage lum_load_foliage(LumRenderer instance, const char* vertex_shader_file, int vertices_per_foliage, int density);
 
+/* -- one frame: start, draw*, prepare, submit (crenderer.cpp:123-166) -- */
 void lum_start_frame(LumRenderer instance);
+void lum_draw_model(LumRenderer instance, const LumMeshModel mesh, const LumMeshTransform* trans);
 void lum_draw_world(LumRenderer instance);
 void lum_draw_particles(LumRenderer instance);
-void lum_draw_model(LumRenderer instance, const LumMeshModel mesh, const LumMeshTransform* trans);
-void lum_draw_foliage_block(LumRenderer instance, const LumMeshFoliage foliage, const int pos[3]);
 void lum_draw_liquid_block(LumRenderer instance, const LumMeshLiquid liquid, const int pos[3]);
 void lum_draw_volumetric_block(LumRenderer instance, const LumMeshVolumetric volumetric, const int pos[3]);
-
+void lum_draw_foliage_block(LumRenderer instance, const LumMeshFoliage foliage, const int pos[3]);
 void lum_prepare_frame(LumRenderer instance);
-void lum_submit_frame(LumRenderer instance);
+void lum_submit_frame(LumRenderer instance);                  /* runs the radiance stage on the GPU */
 
-void lum_cleanup(LumRenderer instance);
-void* lum_get_glfw_ptr(const LumRenderer instance);          /* headless: NULL */
-bool lum_get_should_close(const LumRenderer instance);
+/* -- window state; headless: no window (crenderer.cpp:173-186) -- */
 bool lum_set_should_close(const LumRenderer instance, bool should_close);
-void lum_wait_idle(LumRenderer instance);
+bool lum_get_should_close(const LumRenderer instance);
+void* lum_get_glfw_ptr(const LumRenderer instance);           /* always NULL */
 
-bool lum_is_profiling_enabled(const LumRenderer instance);
+/* -- GPU timestamps: 0 and 1 bracket the radiance dispatch, milliseconds (crenderer.cpp:188-209) -- */
 int lum_get_current_timestamp_count(const LumRenderer instance);
-void lum_get_timestamp_name(const LumRenderer instance, int index, char* out_name, size_t name_length);
-double lum_get_timestamp(const LumRenderer instance, int index);
 double lum_get_timestamp_difference(const LumRenderer instance, int index_start, int index_end);
+double lum_get_timestamp(const LumRenderer instance, int index);
+void lum_get_timestamp_name(const LumRenderer instance, int index, char* out_name, size_t name_length);
+bool lum_is_profiling_enabled(const LumRenderer instance);
 
 /* ---- additions of the headless B200 edition ---------------------------------------------- */
 
