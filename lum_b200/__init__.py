@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblumcu.so")
+LIB_PATH = os.environ.get("LUMCU_LIB") or os.path.join(HERE, "liblumcu.so")   # LUMCU_LIB: tuning builds
 
 DEBUG_PRE_BLEND = 1
 DEBUG_RAYS = 2

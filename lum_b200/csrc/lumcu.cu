@@ -162,10 +162,13 @@ void host_direction_table(int n, std::vector<float> &out) {
 }
 
 // production path: pooled kernel (no z filter); one CTA per 4*threads rays
-template <int R, int T, bool DEBUG>
+#ifndef LUMCU_RPT
+#define LUMCU_RPT 4           // rays per thread of the reference-shaped (R = 64) production kernel
+#endif
+template <int R, int T, int RPT, bool DEBUG>
 int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
-    constexpr int ppc = 4 * T / R;
-    auto k = radiance_update_pool_kernel<R, T, DEBUG>;
+    constexpr int ppc = RPT * T / R;
+    auto k = radiance_update_pool_kernel<R, T, RPT, DEBUG>;
     if (c->carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout);
     dim3 grid((unsigned)((nwg + ppc - 1) / ppc));
     k<<<grid, T, 0, c->stream>>>(sv, a);
@@ -177,12 +180,12 @@ int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long 
 template <bool DEBUG>
 int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
     switch (c->R) {
-        case 16: return launch_pool_one<16, 256, DEBUG>(c, sv, a, nwg);
-        case 32: return launch_pool_one<32, 256, DEBUG>(c, sv, a, nwg);
-        case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, DEBUG>(c, sv, a, nwg)
-                                               : launch_pool_one<64, 256, DEBUG>(c, sv, a, nwg);
-        case 128: return launch_pool_one<128, 256, DEBUG>(c, sv, a, nwg);
-        case 256: return launch_pool_one<256, 256, DEBUG>(c, sv, a, nwg);
+        case 16: return launch_pool_one<16, 256, 4, DEBUG>(c, sv, a, nwg);
+        case 32: return launch_pool_one<32, 256, 4, DEBUG>(c, sv, a, nwg);
+        case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg)
+                                               : launch_pool_one<64, 256, 4, DEBUG>(c, sv, a, nwg);
+        case 128: return launch_pool_one<128, 256, 4, DEBUG>(c, sv, a, nwg);
+        case 256: return launch_pool_one<256, 256, 4, DEBUG>(c, sv, a, nwg);
         default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);
     }
 }
