@@ -15,7 +15,8 @@ Workloads (config.workload):
                         Also measured at N=1 in the default run and reported under "demo".
 
 Timed regions (CUDA events on the stage's stream, L2 flushed between timed steps, max over ranks):
-  value  inputs resident in HBM: update kernel(s) + commit (+ NCCL all-gather when N > 1)
+  value  inputs resident in HBM: update kernel(s) + commit; when N > 1 the commit IS the exchange (peer
+         stores over NVLink between two flag barriers; --exchange nccl = update + NCCL all-gather)
   e2e    through the C-ABI with HOST buffers: world upload (pinned staging) + device request-list
          build + update (+ all-gather) + field download
 The oracle (oracle/) is used here only for the cpu_baseline leg and --impl reference.
@@ -120,7 +121,7 @@ class ClockSampler:
 class Runner:
     """One rank's stage + the per-step sequences (value region and e2e region)."""
 
-    def __init__(self, scene, device, rank, world_size, torch, dist):
+    def __init__(self, scene, device, rank, world_size, torch, dist, exchange="fused"):
         import lum_b200
         from lum_b200 import distributed as D
         self.D = D
@@ -145,14 +146,23 @@ class Runner:
         self.field_host = np.empty(self.cells, np.uint32)
         self.zero_field = np.zeros(self.cells, np.uint32)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")   # > 126 MB L2
+        self.fused = False
+        if world_size > 1 and exchange == "fused":
+            D.open_peer_exchange(self.st, rank, world_size, device=f"cuda:{device}")
+            self.fused = True
 
     def flush_l2(self, k=0):
         with self.torch.cuda.stream(self.stream):
             self.flush.fill_(k & 0xFF)
 
     def reset(self):
+        if self.n > 1:                      # nobody may still be storing into a peer's replica
+            self.st.wait_idle()
+            self.dist.barrier()
         self.st.upload_field(self.zero_field)
         self.st.wait_idle()
+        if self.n > 1:
+            self.dist.barrier()
 
     def exchange(self):
         if self.n > 1:
@@ -160,9 +170,11 @@ class Runner:
                 self.D.all_gather_field(self.field_t, self.dims, self.rank, self.n)
 
     def step_resident(self, seed):
-        if self.n > 1:
+        if self.fused:
+            self.st.update_slab_exchange(seed, 1, 0, self.z0, self.z1)     # commit = exchange (peer stores)
+        elif self.n > 1:
             self.st.update_slab(seed, 1, 0, self.z0, self.z1)
-            self.exchange()
+            self.exchange()                                                # NCCL all-gather
         else:
             self.st.update(seed, 1, 0)
 
@@ -218,7 +230,11 @@ class Runner:
                 b, e = self.st.slab_range(1, 0, self.z0, self.z1)
                 self.st.update_range(first_seed + i, 1, 0, b, e)
                 nwg = e - b
+                if self.fused:      # collective: make sure no peer is still reading before anyone writes
+                    self.st.wait_idle(); self.dist.barrier()
                 self.exchange()
+                if self.fused:
+                    self.st.wait_idle(); self.dist.barrier()
             else:
                 self.st.update(first_seed + i, 1, 0)
                 nwg = self.nreq
@@ -326,7 +342,7 @@ def run_ours(args, rank, local_rank, world_size):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     peak, peak_src = load_peaks()
     scene = make_scene(args.workload)
-    runner = Runner(scene, local_rank, rank, world_size, torch, dist)
+    runner = Runner(scene, local_rank, rank, world_size, torch, dist, exchange=args.exchange)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -352,7 +368,8 @@ def run_ours(args, rank, local_rank, world_size):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": RAYS,
-                           "rays_per_step": m["rays"], "parallelism": f"probe z-slabs x{world_size} + field all-gather"
+                           "rays_per_step": m["rays"], "parallelism": (f"probe z-slabs x{world_size} + " + ("commit fused with the exchange (NVLink peer stores, flag barriers)"
+                                                                              if runner.fused else "NCCL field all-gather"))
                            if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
                            "time_seed": "step index", "initial_field": "zero"},
                 "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"],
@@ -379,6 +396,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synthetic-256x256x64")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: how the ranks exchange their slabs of the field each step")
     ap.add_argument("--no-demo", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -107,6 +107,25 @@ int lumcu_slab_range(LumcuCtx *ctx, int32_t size, int32_t shift, int32_t z_begin
 int lumcu_update_slab(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift,
                       int32_t z_begin, int32_t z_end);
 
+/* ---- multi-GPU exchange over peer memory (one process per GPU; no reference counterpart) --------
+ * Instead of "update the slab, then all-gather", the commit of a slab stores every new texel into the
+ * field replica of EVERY rank through IPC-mapped peer pointers (NVLink P2P), bracketed by two flag
+ * barriers: one launch sequence does the store_probe of radiance.comp:353 and the exchange.
+ *   1. every rank: lumcu_ipc_export(ctx, blob)            (LUMCU_IPC_BYTES bytes)
+ *   2. exchange the blobs out of band (e.g. torch.distributed all_gather)
+ *   3. every rank: lumcu_peers_open(ctx, rank, nranks, blobs)   (nranks x LUMCU_IPC_BYTES bytes, rank order)
+ *   4. per frame, every rank: lumcu_update_slab_exchange(ctx, seed, size, shift, z0, z1) with its slab
+ * All ranks must hold the same world, request list and field; results are bit-identical to
+ * lumcu_update on one GPU.  A rank that stops participating makes the others' barrier time out
+ * (~20 s) and their next call fail with LUMCU_E_STATE instead of hanging. */
+#define LUMCU_IPC_BYTES 128
+#define LUMCU_MAX_PEERS 16
+int lumcu_ipc_export(LumcuCtx *ctx, uint8_t *blob);
+int lumcu_peers_open(LumcuCtx *ctx, int32_t rank, int32_t nranks, const uint8_t *blobs);
+int lumcu_peers_close(LumcuCtx *ctx);
+int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift,
+                               int32_t z_begin, int32_t z_end);
+
 /* shift_radiance (internal_render.cpp:1218-1335): field[p] = field[p + d] over the overlap box. */
 int lumcu_shift(LumcuCtx *ctx, int32_t dx, int32_t dy, int32_t dz);
 

@@ -50,6 +50,10 @@ SYMBOLS = {
                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lumcu_update_slab": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "lumcu_shift": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_ipc_export": (C.c_int, [_P, _P]),
+    "lumcu_peers_open": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "lumcu_peers_close": (C.c_int, [_P]),
+    "lumcu_update_slab_exchange": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "lumcu_upload_model": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "lumcu_free_model": (C.c_int, [_P, C.c_int32]),
     "lumcu_copy_bricks": (C.c_int, [_P, _P, _P, C.c_int32]),
@@ -172,6 +176,23 @@ class RadianceStage:
         self._ck(self.lib.lumcu_slab_range(self.ctx, int(size), int(shift), int(z_begin), int(z_end),
                                            C.byref(b), C.byref(e)))
         return b.value, e.value
+
+    # -- multi-GPU exchange over peer memory -------------------------------------------------
+    def ipc_export(self):
+        blob = np.zeros(128, np.uint8)
+        self._ck(self.lib.lumcu_ipc_export(self.ctx, _ptr(blob)))
+        return blob
+
+    def peers_open(self, rank, blobs):
+        b = np.ascontiguousarray(blobs, np.uint8).reshape(-1, 128)
+        self._ck(self.lib.lumcu_peers_open(self.ctx, int(rank), b.shape[0], _ptr(b)))
+
+    def peers_close(self):
+        self._ck(self.lib.lumcu_peers_close(self.ctx))
+
+    def update_slab_exchange(self, time_seed, size, shift, z_begin, z_end):
+        self._ck(self.lib.lumcu_update_slab_exchange(self.ctx, int(time_seed), int(size), int(shift),
+                                                     int(z_begin), int(z_end)))
 
     def shift(self, dx, dy, dz):
         self._ck(self.lib.lumcu_shift(self.ctx, int(dx), int(dy), int(dz)))

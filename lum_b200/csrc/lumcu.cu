@@ -128,6 +128,18 @@ struct LumcuCtx {
     int2 *d_pairs = nullptr;
     long long pairs_cap = 0;
 
+    // peer exchange (lumcu_peers_open)
+    bool have_peers = false;
+    int peer_rank = 0, peer_n = 1;
+    PeerFields peer_fields{};
+    PeerFlags peer_flags{};
+    void *peer_opened[2 * MAX_PEERS] = {};
+    int n_peer_opened = 0;
+    unsigned *d_sync_flags = nullptr;      // [2][MAX_PEERS] epochs written by the peers
+    unsigned *h_status = nullptr;          // pinned + mapped: barrier timeout flag
+    unsigned *d_status = nullptr;
+    unsigned epoch = 0;
+
     Staging stage_world, stage_req, stage_misc, stage_pairs;
     uint64_t launches = 0;
 };
@@ -220,7 +232,7 @@ int ensure_debug(LumcuCtx *c) {
 }
 
 int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begin, long long wg_end,
-              int z_begin, int z_end) {
+              int z_begin, int z_end, bool commit = true) {
     if (!c->have_world || !c->have_bricks || !c->have_materials)
         return fail(LUMCU_E_STATE, "lumcu_update before world/bricks/materials were uploaded");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
@@ -258,12 +270,33 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             if (int rc = (use_pool ? launch_update_pool<false>(c, sv, a, nwg) : launch_update_R<false>(c, sv, a, nwg))) return rc;
             if (c->profiling) { CU(cudaEventRecord(c->ev_k1, c->stream)); c->ktimed = true; }
         }
-        const int ct = 256;
-        commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
-            c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end);
-        c->launches++;
-        CU(cudaGetLastError());
+        if (commit) {
+            const int ct = 256;
+            commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
+                c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
     }
+    return 0;
+}
+
+int commit_to_peers(LumcuCtx *c, int size, int shift, long long wg_begin, long long wg_end, int z_begin, int z_end) {
+    const long long nwg = wg_end - wg_begin;
+    if (nwg <= 0) return 0;
+    const int ct = 256;
+    commit_peers_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
+        c->peer_fields, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int peer_barrier(LumcuCtx *c, int phase) {
+    // ~20 s at 2 GHz: a rank that died must not hang the others' GPUs
+    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(c->peer_flags, phase, c->epoch, 40000000000ll, c->d_status);
+    c->launches++;
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -342,6 +375,9 @@ int lumcu_destroy(LumcuCtx *c) {
     cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_field);
     cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
     cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
+    lumcu_peers_close(c);
+    cudaFree(c->d_sync_flags);
+    if (c->h_status) cudaFreeHost(c->h_status);
     cudaFree(c->d_special); cudaFree(c->d_bounds); cudaFree(c->d_pairs);
     for (auto &m : c->models) cudaFree(m.d_vox);
     cudaFree(c->d_pre_blend); cudaFree(c->d_ray_samples); cudaFree(c->d_ray_hits); cudaFree(c->d_totals);
@@ -629,6 +665,92 @@ int lumcu_update_slab(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shif
     if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768)) return rc;
     if (tail < nwg_all)   // unsorted tail (specials): every rank scans it, keeps its slab's probes
         if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end)) return rc;
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+int lumcu_ipc_export(LumcuCtx *c, uint8_t *handle) {
+    if (int rc = use(c)) return rc;
+    if (!handle) return fail(LUMCU_E_ARG, "null argument");
+    if (!c->d_sync_flags) {
+        CU(cudaMalloc(&c->d_sync_flags, 2 * MAX_PEERS * sizeof(unsigned)));
+        CU(cudaMemset(c->d_sync_flags, 0, 2 * MAX_PEERS * sizeof(unsigned)));
+        CU(cudaHostAlloc(&c->h_status, sizeof(unsigned), cudaHostAllocMapped));
+        *c->h_status = 0;
+        CU(cudaHostGetDevicePointer(&c->d_status, c->h_status, 0));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->d_field));
+    memcpy(handle, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, c->d_sync_flags));
+    memcpy(handle + 64, &h, 64);
+    return 0;
+}
+
+int lumcu_peers_close(LumcuCtx *c) {
+    if (!c) return 0;
+    if (c->have_peers) {
+        cudaSetDevice(c->desc.device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        for (int i = 0; i < c->n_peer_opened; i++) cudaIpcCloseMemHandle(c->peer_opened[i]);
+    }
+    c->n_peer_opened = 0;
+    c->have_peers = false;
+    return 0;
+}
+
+int lumcu_peers_open(LumcuCtx *c, int32_t rank, int32_t nranks, const uint8_t *handles) {
+    if (int rc = use(c)) return rc;
+    if (nranks < 1 || nranks > MAX_PEERS || rank < 0 || rank >= nranks || !handles)
+        return fail(LUMCU_E_ARG, "bad peer set (rank %d of %d, at most %d ranks)", rank, nranks, MAX_PEERS);
+    if (!c->d_sync_flags) return fail(LUMCU_E_STATE, "lumcu_peers_open before lumcu_ipc_export");
+    lumcu_peers_close(c);
+    c->peer_fields = PeerFields{};
+    c->peer_flags = PeerFlags{};
+    for (int p = 0; p < nranks; p++) {
+        if (p == rank) {
+            c->peer_fields.f[p] = c->d_field;
+            c->peer_flags.f[p] = c->d_sync_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        void *ptr = nullptr;
+        memcpy(&h, handles + 128 * p, 64);
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened[c->n_peer_opened++] = ptr;
+        c->peer_fields.f[p] = (uint32_t *)ptr;
+        memcpy(&h, handles + 128 * p + 64, 64);
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened[c->n_peer_opened++] = ptr;
+        c->peer_flags.f[p] = (unsigned *)ptr;
+    }
+    c->peer_fields.n = nranks;
+    c->peer_flags.n = nranks;
+    c->peer_flags.rank = rank;
+    c->peer_rank = rank; c->peer_n = nranks;
+    c->have_peers = true;
+    return 0;
+}
+
+int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
+    if (int rc = use(c)) return rc;
+    if (!c->have_peers) return fail(LUMCU_E_STATE, "lumcu_update_slab_exchange before lumcu_peers_open");
+    if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
+    int64_t b = 0, e = 0;
+    if (int rc = lumcu_slab_range(c, size, shift, z_begin, z_end, &b, &e)) return rc;
+    const long long nwg_all = c->nreq / size, tail = sorted_workgroups(c, size, shift);
+    c->epoch++;
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768, false)) return rc;
+    if (tail < nwg_all)
+        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false)) return rc;
+    if (int rc = peer_barrier(c, 0)) return rc;             // every rank has finished reading its field
+    if (int rc = commit_to_peers(c, size, shift, b, e, -32768, 32768)) return rc;
+    if (tail < nwg_all)
+        if (int rc = commit_to_peers(c, size, shift, tail, nwg_all, z_begin, z_end)) return rc;
+    if (int rc = peer_barrier(c, 1)) return rc;             // every rank's texels have landed everywhere
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;

@@ -350,6 +350,51 @@ __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__re
         field[rq.x + wx * (rq.y + wy * rq.z)] = staged[w];
 }
 
+// ---- multi-GPU exchange over peer memory (one process per GPU, NVLink P2P) -------------------
+// The commit of a rank's slab is also its part of the all-gather: every staged texel is stored
+// into the field replica of every rank (the local one and the peers' through IPC-mapped pointers),
+// bracketed by two flag barriers (peer_barrier_kernel) instead of a collective call.
+constexpr int MAX_PEERS = 16;
+struct PeerFields { uint32_t *f[MAX_PEERS]; int n; };
+struct PeerFlags { unsigned *f[MAX_PEERS]; int n; int rank; };
+
+__global__ void commit_peers_kernel(PeerFields pf, const uint32_t *__restrict__ staged,
+                                    const short4 *__restrict__ requests, long long wg_begin, long long wg_end,
+                                    int size, int shift, int wx, int wy, int wz, int z_begin, int z_end) {
+    long long w = wg_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= wg_end) return;
+    short4 rq = requests[w * (long long)size + shift];
+    if (rq.z < z_begin || rq.z >= z_end) return;
+    if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz) {
+        const uint32_t word = staged[w];
+        const int cell = rq.x + wx * (rq.y + wy * rq.z);
+#pragma unroll 4
+        for (int p = 0; p < pf.n; p++) pf.f[p][cell] = word;
+    }
+}
+
+// Barrier across the ranks: lane p publishes `epoch` into slot [phase][my rank] of rank p's flag
+// array (after a system-scope fence, so everything this GPU wrote before -- the peer stores of the
+// commit -- is visible first) and then waits until rank p's epoch shows up in the local array.
+// Flags only grow, so no reset is needed.  A rank that never arrives trips the timeout (*status = 1)
+// instead of hanging the GPU.
+__global__ void peer_barrier_kernel(PeerFlags pf, int phase, unsigned epoch, long long timeout_cycles,
+                                    volatile unsigned *status) {
+    const int p = threadIdx.x;
+    if (p < pf.n) {
+        __threadfence_system();
+        volatile unsigned *dst = pf.f[p] + phase * MAX_PEERS + pf.rank;
+        *dst = epoch;
+        volatile unsigned *src = pf.f[pf.rank] + phase * MAX_PEERS + p;
+        const long long t0 = clock64();
+        while ((int)(*src - epoch) < 0) {
+            __nanosleep(100);
+            if (clock64() - t0 > timeout_cycles) { *status = 1u; break; }
+        }
+    }
+    __threadfence_system();
+}
+
 // shift_radiance (internal_render.cpp:1218-1335): field[p] = tmp[p + d] on the overlap box.
 __global__ void shift_kernel(uint32_t *__restrict__ field, const uint32_t *__restrict__ tmp,
                              int wx, int wy, int wz, int dx, int dy, int dz) {

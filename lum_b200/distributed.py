@@ -4,8 +4,10 @@ Design: the read-only world / palette / materials are rep
 rank; the field is replicated too and updated Jacobi-style.  Rank r of N owns the contiguous
 z-slab [r*Z/N, (r+1)*Z/N) of the field (the field is z-major, so a slab is one contiguous range of
 words), updates exactly the probes of that slab (lumcu_update_slab) and then all ranks exchange
-their slabs with ONE in-place all-gather, after which every rank holds the identical new field for
-the next frame's gathers.  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
+their slabs -- either with ONE in-place all-gather (all_gather_field), or fused into the commit itself:
+lumcu_update_slab_exchange stores every new texel straight into all ranks' field replicas over NVLink
+peer memory between two flag barriers (open_peer_exchange wires it) -- after which every rank holds the
+identical new field for the next frame's gathers.  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
 CPU for the tests of this host-side logic).
 """
 from __future__ import annotations
@@ -53,3 +55,24 @@ def device_tensor_view(ptr: int, nwords: int, device):
         __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i4", "data": (ptr, False), "version": 3}
 
     return torch.as_tensor(_Iface(), device=device)
+
+
+def open_peer_exchange(stage, rank: int, world_size: int, device=None, group=None):
+    """Wire the fused commit+exchange (lumcu_update_slab_exchange): export this rank's IPC blob,
+    all-gather the blobs through torch.distributed (NCCL: a small uint8 device tensor; gloo: CPU) and
+    open the peers' field / flag buffers.  Every rank must call it (collective)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    blob = stage.ipc_export()
+    if world_size == 1:
+        stage.peers_open(0, blob.reshape(1, -1))
+        return
+    t = torch.from_numpy(blob.copy())
+    if device is not None:
+        t = t.to(device)
+    out = torch.empty(world_size * t.numel(), dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    blobs = out.cpu().numpy().reshape(world_size, -1)
+    stage.peers_open(rank, blobs)
+    dist.barrier(group=group)        # nobody starts exchanging before everyone has mapped everyone

@@ -37,6 +37,15 @@ for f in range(4):
         D.all_gather_field(field, (wx, wy, wz), rank, world)
 out = st.download_field()
 np.save(os.path.join(os.environ["OUT_DIR"], f"f{rank}.npy"), out)
+# the same four frames with the exchange fused into the commit (peer stores + flag barriers)
+st.upload_field(np.zeros(st.cells, np.uint32)); st.wait_idle(); dist.barrier()
+D.open_peer_exchange(st, rank, world, device=f"cuda:{rank}")
+for f in range(4):
+    st.update_slab_exchange(f, 1, 0, z0, z1)
+out = st.download_field()
+dist.barrier()
+np.save(os.path.join(os.environ["OUT_DIR"], f"g{rank}.npy"), out)
+st.peers_close()
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -64,3 +73,22 @@ def test_two_gpu_slabs_match_single_gpu(tmp_path):
     a, b = np.load(tmp_path / "f0.npy"), np.load(tmp_path / "f1.npy")
     assert np.array_equal(a, b)
     assert np.array_equal(a, ref)
+    ga, gb = np.load(tmp_path / "g0.npy"), np.load(tmp_path / "g1.npy")
+    assert np.array_equal(ga, ref) and np.array_equal(gb, ref)        # fused exchange: same bits
+
+
+def test_peer_exchange_single_rank_degenerates_to_update(oracle_mod, demo):
+    """nranks = 1: the peer commit writes only the local replica and the barriers are trivial."""
+    from conftest import make_stage
+    from lum_b200 import distributed as D
+    st = make_stage(demo)
+    n = st.build_requests(np.array([(7, 9, 2, 0), (40, 40, 14, 0)], np.int16))
+    D.open_peer_exchange(st, 0, 1)
+    for f in range(3):
+        st.update_slab_exchange(f, 1, 0, 0, 16)
+    got = st.download_field()
+    st.upload_field(np.zeros(st.cells, np.uint32))
+    for f in range(3):
+        st.update(f)
+    assert np.array_equal(got, st.download_field())
+    st.peers_close()
