@@ -53,6 +53,20 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(workload, n_gpus):
+    """DRAM bytes per launch of the trace kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture, profiles/roofline_traffic.json, written by tools/ncu_traffic.py).
+    Only the single-GPU launch was captured; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        t = json.load(open(p))
+        if n_gpus == 1 and workload in t:
+            return float(t[workload]["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def make_scene(workload):
     from lum_b200 import scenes
     if workload == "demo":
@@ -142,8 +156,13 @@ class Runner:
         self.stream = torch.cuda.ExternalStream(self.st.stream(), device=device)
         self.dims = (wx, wy, wz)
         self.field_t = D.device_tensor_view(self.st.field_device_ptr(), self.cells, f"cuda:{device}")
-        self.world_host = np.ascontiguousarray(scene["world"], np.int16)
-        self.field_host = np.empty(self.cells, np.uint32)
+        # e2e host buffers live in pinned memory (the contract's "from pinned host memory"): the world
+        # goes up without a staging copy and the field comes down at full PCIe rate
+        self._pin_w = torch.empty(self.cells, dtype=torch.int16, pin_memory=True)
+        self._pin_f = torch.empty(self.cells, dtype=torch.int32, pin_memory=True)
+        self.world_host = self._pin_w.numpy()
+        self.world_host[:] = np.ascontiguousarray(scene["world"], np.int16).reshape(-1)
+        self.field_host = self._pin_f.numpy().view(np.uint32)
         self.zero_field = np.zeros(self.cells, np.uint32)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")   # > 126 MB L2
         self.fused = False
@@ -183,9 +202,11 @@ class Runner:
         self.st.build_requests()                              # device builder (+8 B count readback)
         self.step_resident(seed)
         if self.n > 1:                                        # D2H: each rank reads its slab of the result
+            lo, hi = self.rank * self.slab_cells, (self.rank + 1) * self.slab_cells
             with self.torch.cuda.stream(self.stream):
-                t = self.field_t[self.rank * self.slab_cells:(self.rank + 1) * self.slab_cells].cpu()
-            return t
+                self._pin_f[lo:hi].copy_(self.field_t[lo:hi], non_blocking=True)
+            self.st.wait_idle()
+            return self.field_host[lo:hi]
         self.st.download_field(self.field_host)
         return self.field_host
 
@@ -358,7 +379,7 @@ def run_ours(args, rank, local_rank, world_size):
                          "e2e": {"value": dm["e2e_value"], "unit": UNIT, "ms_per_step": dm["e2e_ms"],
                                  "h2d_bytes_per_step": dm["h2d"], "d2h_bytes_per_step": dm["d2h"]},
                          "roofline": {"bound": "hbm", "achieved": dm["achieved"], "peak": peak, "unit": "GB/s",
-                                      "frac": dm["frac"], "traffic": None}}
+                                      "frac": dm["frac"], "traffic": load_traffic("demo", 1)}}
     if rank == 0:
         cb = None
         if world_size == 1 and not args.no_cpu:
@@ -376,7 +397,7 @@ def run_ours(args, rank, local_rank, world_size):
                         "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
                 "gpu_launches": m["launches"],
                 "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
-                             "frac": m["frac"], "traffic": None, "peak_source": peak_src,
+                             "frac": m["frac"], "traffic": load_traffic(args.workload, world_size), "peak_source": peak_src,
                              "kernel": "radiance_update kernel", "kernel_ms": m["kernel_ms"],
                              "algorithmic_bytes_per_launch": m["alg_bytes"]},
                 "clocks": clocks}

@@ -79,6 +79,8 @@ struct LumcuCtx {
     long long cells = 0;
     long long max_requests = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // uploads from caller-pinned memory (no staging copy)
+    cudaEvent_t ev_compute = nullptr, ev_copy = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     bool timed = false, profiling = false, ktimed = false;
 
@@ -337,6 +339,9 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(LUMCU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
     CUB(cudaSetDevice(d->device));
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     CUB(cudaEventCreate(&c->ev_begin));
     CUB(cudaEventCreate(&c->ev_end));
     CUB(cudaEventCreate(&c->ev_k0));
@@ -386,12 +391,30 @@ int lumcu_destroy(LumcuCtx *c) {
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
     if (c->ev_k1) cudaEventDestroy(c->ev_k1);
+    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
 
 static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, size_t bytes) {
+    // Caller buffer already page-locked (cudaHostAlloc / cudaHostRegister): copy straight from it on
+    // the copy stream -- ordered after the work already queued (the kernels still reading dst) and
+    // before whatever is queued next -- and return once the copy itself is done, so the buffer is
+    // consumed before the call returns without a host-side staging memcpy.
+    cudaPointerAttributes attr{};
+    if (bytes >= (64u << 10) && cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        CU(cudaEventRecord(c->ev_compute, c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_compute, 0));
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+        CU(cudaEventSynchronize(c->ev_copy));
+        return 0;
+    }
+    cudaGetLastError();   // cudaPointerGetAttributes on plain pageable memory may leave an error state on old drivers
     void *h; int slot;
     if (int rc = st.acquire(bytes, &h, &slot)) return rc;
     memcpy(h, src, bytes);

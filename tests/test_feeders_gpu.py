@@ -298,3 +298,27 @@ def test_api_file_loaders_and_shift(oracle_mod, demo, tmp_path):
     assert np.array_equal(r.download_field(), f1)
     r.free_mesh(h)
     r.close()
+
+
+def test_pinned_host_buffers_upload_directly(oracle_mod, small_synth):
+    """A page-locked caller buffer is copied without the staging memcpy (lumcu.cu staged_upload);
+    same device contents, and the buffer may be overwritten as soon as the call returns."""
+    import torch
+    O = oracle_mod
+    sc = small_synth
+    big = np.tile(sc["world"], (1, 4, 4))                                   # > 64 KiB: takes the direct path
+    st = make_stage(dict(world=big, bricks=sc["bricks"], materials=sc["materials"]))
+    pin = torch.empty(big.size, dtype=torch.int16, pin_memory=True)
+    pin.numpy()[:] = big.reshape(-1)
+    st.upload_world(pin.numpy())
+    pin.numpy()[:] = 0                                                      # consumed before return
+    assert np.array_equal(st.download_world(), big)
+    n = st.build_requests()
+    req = O.build_requests(big)
+    assert n == len(req)
+    scn = O.Scene(big, sc["bricks"], sc["materials"])
+    ref = O.update(scn, np.zeros(scn.cells, np.uint32), req, 3)
+    st.update(3)
+    out = torch.empty(big.size, dtype=torch.int32, pin_memory=True)
+    got = st.download_field(out.numpy().view(np.uint32))
+    assert np.array_equal(got, ref["field"])
