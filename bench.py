@@ -303,6 +303,46 @@ def measure(runner, steps, warmup, peak):
                 probes=runner.nreq, rays=total_rays)
 
 
+def measure_api_config3(frames=64, warmup=8):
+    """BASELINE configs[2] through Lum's own C API (include/clum.h, liblum.so): the demo world with two
+    mapped models moving every frame -- blockify, world upload, brick copies, map, request rebuild and a
+    full radiance update per lum_submit_frame.  Wall clock over `frames` frames, host included."""
+    import math
+    from lum_b200 import clum, scenes
+    d = scenes.demo_scene()
+    r = clum.Renderer((48, 48, 16), 15, profile=False)
+    r.load_world(d["world"])
+    for i in range(1, 15):
+        r.load_block(i, d["bricks"][i])
+    r.set_material_palette(d["materials"])
+    r.upload_block_palette(); r.upload_material_palette()
+    r.set_radiance_controller(False, 1)                      # every probe every frame
+    ha, hb = r.load_mesh_data(d["model_tank_body"]), r.load_mesh_data(d["model_tank_head"])
+    hz = d["model_tank_body"].shape[0]
+
+    def frame(f):
+        a = 0.05 * f
+        base = (13.1 * 16 + 0.75 * (f % 16), 14.1 * 16 + 0.5 * (f % 16), 3.1 * 16)
+        r.start_frame(); r.draw_world()
+        r.draw_model(ha, (math.cos(a / 2), 0, 0, math.sin(a / 2)), base)
+        r.draw_model(hb, (math.cos(-a), 0, 0, math.sin(-a)), (base[0] + 2, base[1] + 3, base[2] + hz))
+        r.prepare_frame(); r.submit_frame()
+
+    for f in range(warmup):
+        frame(f)
+    r.wait_idle()
+    t0 = time.perf_counter()
+    for f in range(frames):
+        frame(warmup + f)
+    r.wait_idle()
+    dt = time.perf_counter() - t0
+    n = r.request_count()
+    r.close()
+    return {"workload": "demo world + tank_body/tank_head moving each frame, via lum_submit_frame (BASELINE configs[2])",
+            "frames": frames, "ms_per_frame": dt / frames * 1e3, "probes_per_frame": int(n),
+            "value": n * RAYS * frames / dt, "unit": UNIT, "timing": "host wall clock, includes the host side of the API"}
+
+
 def cpu_baseline(scene, budget_s, threads=0):
     """The oracle port on the host cores, on a bounded strided sample of the request list."""
     import oracle as O
@@ -373,6 +413,12 @@ def run_ours(args, rank, local_rank, world_size):
     if rank == 0 and world_size == 1 and args.workload != "demo" and not args.no_demo:
         dr = Runner(make_scene("demo"), local_rank, 0, 1, torch, dist)
         dm = measure(dr, max(args.steps, 20), max(args.warmup, 5), peak)
+        try:     # in a child process: the API mirror abort()s on errors (reference behaviour) and must not take the bench down
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--api-config3"], capture_output=True,
+                               text=True, timeout=300, env=dict(os.environ, LUM_B200_DEVICE=str(local_rank)))
+            extra["config3_api"] = json.loads(p.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            extra["config3_api"] = {"error": repr(e)}
         extra["demo"] = {"workload": "demo (BASELINE configs[1]: 48x48x16 demo world, full recompute)",
                          "probes": dm["probes"], "rays": dm["rays"], "value": dm["value"], "unit": UNIT,
                          "ms_per_step": dm["ms_per_step"], "kernel_ms": dm["kernel_ms"],
@@ -421,7 +467,11 @@ def main():
                     help="N>1: how the ranks exchange their slabs of the field each step")
     ap.add_argument("--no-demo", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--api-config3", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.api_config3:
+        print(json.dumps(measure_api_config3()), flush=True)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -103,16 +103,23 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
 // own (o, d, t) only, and the reduction tree is fixed.
 struct PoolRay { f3 o, d, inv; float t; int ns; };
 
+// Ray slots, packed for 16-byte shared-memory accesses: a = (o.xyz, t), b = (d.xyz, inv.x),
+// c = (inv.yz).  A refill is 2 x LDS.128 + 1 x LDS.64 instead of ten scalar loads; consecutive slots
+// keep every quarter-warp conflict-free.  After shading, a.xyz holds the ray's light.
 template <int NR, bool DEBUG>
 struct PoolShared {
-    float o[3][NR], d[3][NR], inv[3][NR], t[NR];
+    float4 a[NR];
+    float4 b[NR];
+    float2 c[NR];
     unsigned char done[NR];               // 1 = terminated during pass 0 (shaded by the chunk loop)
     unsigned short ns[DEBUG ? NR : 1];    // marching samples so far (instrumented variant only)
     __device__ __forceinline__ void load(int r, PoolRay &q) const {
-        q.o = {o[0][r], o[1][r], o[2][r]};
-        q.d = {d[0][r], d[1][r], d[2][r]};
-        q.inv = {inv[0][r], inv[1][r], inv[2][r]};
-        q.t = t[r];
+        const float4 va = a[r], vb = b[r];
+        const float2 vc = c[r];
+        q.o = {va.x, va.y, va.z};
+        q.d = {vb.x, vb.y, vb.z};
+        q.inv = {vb.w, vc.x, vc.y};
+        q.t = va.w;
         if constexpr (DEBUG) q.ns = ns[r];
     }
 };
@@ -164,7 +171,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                     base = __shfl_sync(FULL, base, 0);
                     if (cur >= 0) {
                         dst[base + __popc(~idle & ((1u << lane) - 1u))] = (unsigned short)cur;
-                        sm.t[cur] = q.t;
+                        sm.a[cur].w = q.t;
                         if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                     }
                     break;
@@ -175,7 +182,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
             const int st = march_step(s, mc, q.o, q.d, q.inv, q.t);
             q.ns++;
             if (st) {
-                sm.t[cur] = st == 1 ? q.t : -q.t;                  // sign = miss (t >= 0.5 always)
+                sm.a[cur].w = st == 1 ? q.t : -q.t;                // sign = miss (t >= 0.5 always)
                 if (mark_done) sm.done[cur] = 1;
                 if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                 cur = -1;
@@ -194,7 +201,7 @@ __device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const Scen
     const bool hit = q.t > 0.0f;
     int nr;
     const f3 l = finish_ray(s, q.o, q.d, q.inv, fabsf(q.t), hit, sun, nr);
-    sm.o[0][r] = l.x; sm.o[1][r] = l.y; sm.o[2][r] = l.z;
+    sm.a[r].x = l.x; sm.a[r].y = l.y; sm.a[r].z = l.z;
     if constexpr (DEBUG) {
         const unsigned nsamp = (unsigned)q.ns + (unsigned)nr;
         if (a.dbg_samples) a.dbg_samples[wg0 * R + r] = nsamp;
@@ -239,10 +246,9 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
         const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
         f3 o, d, inv;
         setup_ray(rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, o, d, inv);
-        sm.o[0][r] = o.x; sm.o[1][r] = o.y; sm.o[2][r] = o.z;
-        sm.d[0][r] = d.x; sm.d[1][r] = d.y; sm.d[2][r] = d.z;
-        sm.inv[0][r] = inv.x; sm.inv[1][r] = inv.y; sm.inv[2][r] = inv.z;
-        sm.t[r] = 0.0f;
+        sm.a[r] = make_float4(o.x, o.y, o.z, 0.0f);
+        sm.b[r] = make_float4(d.x, d.y, d.z, inv.x);
+        sm.c[r] = make_float2(inv.y, inv.z);
         sm.done[r] = 0;
         if constexpr (DEBUG) sm.ns[r] = 0;
     }
@@ -307,7 +313,8 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
 #pragma unroll
         for (int g = 0; g < NSUB; g++) {
             const int r = pr * R + g * SUB + lane;
-            float lx = lane < SUB ? sm.o[0][r] : 0.0f, ly = lane < SUB ? sm.o[1][r] : 0.0f, lz = lane < SUB ? sm.o[2][r] : 0.0f;
+            const float4 lv = lane < SUB ? sm.a[r] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float lx = lv.x, ly = lv.y, lz = lv.z;
 #pragma unroll
             for (int k = SUB / 2; k >= 1; k >>= 1) {
                 lx += __shfl_xor_sync(FULL, lx, k);
