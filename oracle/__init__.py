@@ -19,13 +19,12 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the oracle (and oracle/_ref when the reference tree is present)."""
-    src = os.path.join(_HERE, "lum_oracle.c")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("lum_oracle.c", "lum_oracle_feeders.c", "lum_oracle.h", "Makefile"))
-    if force or stale:
-        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
-    assert os.path.exists(src)
+    # make decides what is stale; the _ref targets are attempted only where /root/reference exists
+    args = ["make", "-C", _HERE] + (["-B"] if force else []) + ["all"]
+    r = subprocess.run(args, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    assert os.path.exists(_LIB_PATH)
     return _LIB_PATH
 
 
@@ -149,7 +148,7 @@ def trace(scene: Scene, field, probe, gid_x, ray_index, time_seed, table=None):
 
 def update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, nthreads=0,
            want_rays=False, wg_range=None):
-    """Returns dict(field, pre_blend, totals=(S,H,N), threads[, ray_samples, ray_hits])."""
+    """Returns dict(field, pre_blend, totals=(S,H,N), threads[, ray_samples, ray_hits, ray_coarse])."""
     field_old = np.ascontiguousarray(field_old, np.uint32).reshape(-1)
     assert field_old.size == scene.cells
     req = np.ascontiguousarray(requests, np.int16).reshape(-1, 4)
@@ -159,17 +158,19 @@ def update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, nthrea
     pre = np.zeros((nwg, 3), np.float32)
     rs = np.zeros(nwg * scene.rays, np.uint32) if want_rays else None
     rh = np.zeros(nwg * scene.rays, np.uint8) if want_rays else None
+    rcs = np.zeros(nwg * scene.rays, np.uint16) if want_rays else None
     tot = (C.c_uint64 * 3)()
     b, e = (0, -1) if wg_range is None else wg_range
     used = lib().lum_oracle_update_ex(C.byref(scene.c), _p(field_old), _p(field_new), _p(req),
                                       C.c_int64(nreq), C.c_int(time_seed), C.c_int(size), C.c_int(shift),
-                                      _p(pre), _p(rs), _p(rh), None, tot, C.c_int(nthreads),
+                                      _p(pre), _p(rs), _p(rh), _p(rcs), tot, C.c_int(nthreads),
                                       C.c_int64(b), C.c_int64(e))
     res = dict(field=field_new, pre_blend=pre, totals=(int(tot[0]), int(tot[1]), int(tot[2])),
                threads=used)
     if want_rays:
         res["ray_samples"] = rs
         res["ray_hits"] = rh
+        res["ray_coarse"] = rcs
     return res
 
 
@@ -237,3 +238,45 @@ def map_model(world, bricks, model, placement, static_count):
     lib().lum_oracle_map_model(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(w), _p(bricks), C.c_int(bricks.shape[0]),
                                _p(m), C.c_int(sx), C.c_int(sy), C.c_int(sz), placement.inverse_trans,
                                placement.map_shift, placement.map_area, C.c_int(static_count))
+
+
+# ---- oracle/_ref: the reference's own radiance.comp executed on the CPU -----------------------
+# (oracle/ref_radiance_glsl.cpp; built only where /root/reference exists, travels as a built .so)
+_REF_GLSL_PATH = os.path.join(_HERE, "_ref", "libref_radiance_glsl.so")
+_ref_glsl = None
+
+
+def ref_glsl_available() -> bool:
+    return os.path.exists(_REF_GLSL_PATH)
+
+
+def ref_glsl_update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, want_rays=False):
+    """One dispatch of the reference's shaders/radiance.comp (its own text, compiled through
+    oracle/glsl_shim.hpp).  Same inputs as update(); request coordinates must fit the reference's
+    i8vec4 (<= 127).  Returns dict(field, pre_blend[, ray_light, ray_fetches]) where
+    ray_fetches = texelFetch(blocks) calls per invocation = 2 + 2*coarse + refinement samples."""
+    global _ref_glsl
+    if _ref_glsl is None:
+        _ref_glsl = C.CDLL(_REF_GLSL_PATH)
+        _ref_glsl.ref_glsl_radiance_update.restype = C.c_int
+    assert scene.rays == 64, "the reference defines RAYS_PER_PROBE = 64 only"
+    field_old = np.ascontiguousarray(field_old, np.uint32).reshape(-1)
+    assert field_old.size == scene.cells
+    req16 = np.ascontiguousarray(requests, np.int16).reshape(-1, 4)
+    assert req16.size == 0 or (req16.max() <= 127 and req16.min() >= -128)
+    req = np.ascontiguousarray(req16.astype(np.int8))
+    nwg = req.shape[0] // size
+    field_new = np.empty_like(field_old)
+    pre = np.zeros((nwg, 3), np.float32)
+    rl = np.zeros((nwg * 64, 3), np.float32) if want_rays else None
+    rf = np.zeros(nwg * 64, np.uint32) if want_rays else None
+    rc = _ref_glsl.ref_glsl_radiance_update(
+        C.c_int(scene.wx), C.c_int(scene.wy), C.c_int(scene.wz), _p(scene.world), _p(scene.bricks),
+        C.c_int(scene.bricks.shape[0]), _p(scene.materials), _p(field_old), _p(field_new), _p(req),
+        C.c_long(req.shape[0]), C.c_int(time_seed), C.c_int(size), C.c_int(shift), _p(pre), _p(rl), _p(rf))
+    assert rc == 0, rc
+    res = dict(field=field_new, pre_blend=pre)
+    if want_rays:
+        res["ray_light"] = rl
+        res["ray_fetches"] = rf
+    return res

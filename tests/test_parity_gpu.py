@@ -13,6 +13,8 @@ from lum_b200 import DEBUG_PRE_BLEND, DEBUG_RAYS, scenes
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "oracle_demo_golden.npz")
+REF_GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_glsl_golden.npz")
+REF_REL_TOL = 1e-6      # see tests/test_ref_glsl.py: texture-coordinate un-normalisation in the shim
 
 
 def bits(a):
@@ -87,6 +89,33 @@ def test_demo_golden_vectors(demo):
         assert d["totals"] == tuple(int(v) for v in g["totals"][frame])
         assert np.array_equal(d["pre_blend"][g["probe_idx"]], g["pre_blend"][frame])
     assert np.array_equal(st.download_field(), g["field"])
+
+
+@pytest.mark.parametrize("tag", ["demo", "demo3", "synth"])
+def test_reference_shader_golden_vectors(demo, tag):
+    """CUDA against the outputs of the reference's OWN shaders/radiance.comp (executed on the CPU in
+    the build container, tests/golden/make_ref_glsl_golden.py); no oracle code runs here.
+    Packed field words equal; pre-blend radiance within REF_REL_TOL*max(1,|x|)."""
+    g = np.load(REF_GOLD)
+    scn = demo if tag.startswith("demo") else scenes.synthetic_scene(24, 24, 8, palette=64)
+    st = make_stage(scn)
+    n = st.build_requests()
+    req = g[f"{tag}_requests"]
+    assert n == len(req) and np.array_equal(st.download_requests(), req)
+    size = int(g[f"{tag}_size"])
+    for variant in (1, 0):
+        st.set_kernel_variant(variant)
+        for frame in (int(f) for f in g[f"{tag}_frames"]):
+            st.upload_field(g[f"{tag}_before_{frame}"])
+            st.set_debug(DEBUG_PRE_BLEND)
+            st.update(frame, size, frame % size)
+            pre = st.download_debug(n // size)["pre_blend"]
+            want = g[f"{tag}_pre_{frame}"]
+            assert np.all(np.abs(pre - want) <= REF_REL_TOL * np.maximum(1.0, np.abs(want))), (tag, frame)
+            assert np.array_equal(st.download_field(), g[f"{tag}_after_{frame}"]), (tag, frame)
+            if frame == 0:      # zero field: nothing is left to tolerance
+                assert np.array_equal(pre, want), (tag, frame)
+    st.set_kernel_variant(1)
 
 
 @pytest.mark.parametrize("seed", [0, 2, 77, 2 ** 31 - 1, -5])

@@ -1,0 +1,112 @@
+"""The oracle pinned against the REFERENCE's own shader.
+
+oracle/_ref/libref_radiance_glsl.so is shaders/radiance.comp itself -- read where it lies under
+/root/reference, token-rewritten by oracle/glsl_prep.py and compiled as C++ on oracle/glsl_shim.hpp
+-- executed on the CPU.  tests/golden/ref_glsl_golden.npz holds its outputs
+(tests/golden/make_ref_glsl_golden.py).  Here the C restatement (oracle/lum_oracle.c), which is
+what the CUDA path is compared with bit for bit, is checked against those vectors, and -- where
+the _ref library is present -- against live runs of the shader on other inputs.
+
+Bar: packed field words EQUAL; per-invocation sample counts EQUAL (integer work); per-probe
+pre-blend mean radiance within REL_TOL*max(1,|x|).  The tolerance exists for one reason: the shim's
+textureLod un-normalises the coordinate in f32 (u*size - 0.5, as a driver would) while the
+restatement uses the algebraically equal block-space coordinate directly, so filter weights can
+differ in their last bits.  Observed worst case 1.7e-7; the north_star bar is 1e-5."""
+import os
+
+import numpy as np
+import pytest
+
+from lum_b200 import scenes
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_glsl_golden.npz")
+REL_TOL = 1e-6
+
+
+def close(a, b):
+    return np.all(np.abs(a - b) <= REL_TOL * np.maximum(1.0, np.abs(b)))
+
+
+def chain_scene(O, tag, demo):
+    if tag.startswith("demo"):
+        return O.Scene(demo["world"], demo["bricks"], demo["materials"])
+    s = scenes.synthetic_scene(24, 24, 8, palette=64)
+    return O.Scene(s["world"], s["bricks"], s["materials"])
+
+
+@pytest.mark.parametrize("tag", ["demo", "demo3", "synth"])
+def test_oracle_matches_reference_shader_golden(oracle_mod, demo, tag):
+    O = oracle_mod
+    g = np.load(GOLD)
+    sc = chain_scene(O, tag, demo)
+    req = g[f"{tag}_requests"]
+    assert np.array_equal(req, O.build_requests(sc.world))          # a13 request order
+    size = int(g[f"{tag}_size"])
+    for frame in (int(f) for f in g[f"{tag}_frames"]):
+        r = O.update(sc, g[f"{tag}_before_{frame}"], req, frame, size=size, shift=frame % size, want_rays=True)
+        assert np.array_equal(r["field"], g[f"{tag}_after_{frame}"]), (tag, frame)
+        assert close(r["pre_blend"], g[f"{tag}_pre_{frame}"]), (tag, frame)
+        key = f"{tag}_fetches_{frame}"
+        if key in g.files:
+            # texelFetch(blocks) per invocation: 2 dead at the origin (radiance.comp:195-196), 2 per
+            # coarse iteration (:213-214), 1 per refinement sample (:267,280)
+            mine = 2 + r["ray_coarse"].astype(np.int64) + r["ray_samples"].astype(np.int64)
+            assert np.array_equal(mine, g[key].astype(np.int64)), (tag, frame)
+
+
+def test_golden_zero_field_frames_are_bit_equal(oracle_mod, demo):
+    """With a zero field the gather contributes exact zeros, so nothing is left to tolerance."""
+    O = oracle_mod
+    g = np.load(GOLD)
+    for tag in ("demo", "synth"):
+        sc = chain_scene(O, tag, demo)
+        r = O.update(sc, g[f"{tag}_before_0"], g[f"{tag}_requests"], 0)
+        assert np.array_equal(r["pre_blend"], g[f"{tag}_pre_0"])
+
+
+needs_ref = pytest.mark.skipif(not __import__("oracle").ref_glsl_available(),
+                               reason="oracle/_ref not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 5, 2 ** 31 - 1, -3])
+def test_oracle_matches_live_reference_shader_random_field(oracle_mod, demo, seed):
+    O = oracle_mod
+    sc = chain_scene(O, "demo", demo)
+    rng = np.random.default_rng(seed & 0xFFFF)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    req = O.build_requests(demo["world"])
+    # specials appended out of order, as demo.cpp:212 does
+    req = np.concatenate([req, np.array([[0, 0, 15, 0], [47, 47, 0, 0], [5, 40, 9, 0]], np.int16)])
+    ref = O.ref_glsl_update(sc, f0, req, seed, want_rays=True)
+    r = O.update(sc, f0, req, seed, want_rays=True)
+    assert np.array_equal(r["field"], ref["field"])
+    assert close(r["pre_blend"], ref["pre_blend"])
+    assert np.array_equal(2 + r["ray_coarse"].astype(np.int64) + r["ray_samples"], ref["ray_fetches"])
+
+
+@needs_ref
+def test_oracle_matches_live_reference_shader_edge_world(oracle_mod):
+    """Tiny 3x2x1 world: every ray leaves through a face within a few cells (low-face re-sample and
+    high-face out-of-range fetch of SURVEY A.12), solid ground brick, emissive material."""
+    O = oracle_mod
+    world = np.zeros((1, 2, 3), np.int16)
+    world[0, 0, 0] = 1
+    world[0, 1, 2] = 2
+    bricks = np.zeros((3, 16, 16, 16), np.uint8)
+    bricks[1] = 7
+    bricks[2, 4:12, 4:12, 4:12] = 9
+    mats = np.zeros((256, 6), np.float32)
+    mats[7] = (0.9, 0.5, 0.1, 1, 0, 1)
+    mats[9] = (0.2, 0.8, 0.9, 1, 6.0, 0.5)
+    sc = O.Scene(world, bricks, mats)
+    req = np.array([[x, y, 0, 0] for y in range(2) for x in range(3)], np.int16)
+    f = np.zeros(sc.cells, np.uint32)
+    for frame in range(6):
+        ref = O.ref_glsl_update(sc, f, req, frame, want_rays=True)
+        r = O.update(sc, f, req, frame, want_rays=True)
+        assert np.array_equal(r["field"], ref["field"]), frame
+        assert close(r["pre_blend"], ref["pre_blend"]), frame
+        assert np.array_equal(2 + r["ray_coarse"].astype(np.int64) + r["ray_samples"], ref["ray_fetches"]), frame
+        f = ref["field"]
+    assert np.count_nonzero(f & 0x3FFFFFFF) > 0
