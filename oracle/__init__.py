@@ -1,6 +1,7 @@
 """ctypes wrapper around the CPU oracle (oracle/lum_oracle.c).
 
-TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see oracle/lum_oracle.h).  Only tests/,
+TEST INFRASTRUCTURE ONLY -- pinned against the reference's own shaders run on the CPU (see
+oracle/lum_oracle.h; host-side feeders remain unpinned).  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
 module.  The product package (lum_b200) never does.
 """
@@ -280,3 +281,29 @@ def ref_glsl_update(scene: Scene, field_old, requests, time_seed, size=1, shift=
         res["ray_light"] = rl
         res["ray_fetches"] = rf
     return res
+
+
+_REF_MAP_PATH = os.path.join(_HERE, "_ref", "libref_map_glsl.so")
+_ref_map = None
+
+
+def ref_map_available() -> bool:
+    return os.path.exists(_REF_MAP_PATH)
+
+
+def ref_glsl_map_model(world, bricks, model, placement):
+    """One map_mesh dispatch of the reference's own shaders/map.comp (oracle/ref_map_glsl.cpp);
+    same arguments as map_model().  The shader hard-codes STATIC_BLOCK_COUNT = 15 (map.comp:22)."""
+    global _ref_map
+    if _ref_map is None:
+        _ref_map = C.CDLL(_REF_MAP_PATH)
+        _ref_map.ref_glsl_map_model.restype = C.c_int
+    w = np.ascontiguousarray(world, np.int16)
+    wz, wy, wx = w.shape
+    m = np.ascontiguousarray(model, np.uint8)
+    sz, sy, sx = m.shape
+    assert bricks.flags.c_contiguous and bricks.dtype == np.uint8
+    rc = _ref_map.ref_glsl_map_model(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(w), _p(bricks), C.c_int(bricks.shape[0]),
+                                     _p(m), C.c_int(sx), C.c_int(sy), C.c_int(sz), placement.inverse_trans,
+                                     placement.map_shift, placement.map_area)
+    assert rc == 0, rc

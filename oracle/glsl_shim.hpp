@@ -93,14 +93,24 @@ template <class T> struct tvec4 {
     tvec4() : x(), y(), z(), w() {}
     tvec4(T a_, T b_, T c, T d) : x(a_), y(b_), z(c), w(d) {}
     template <class S> tvec4(const tvec3<T>& v, S d) : x(v.x), y(v.y), z(v.z), w((T)d) {}
+    T& operator[](int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+    T operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
     tvec3<T> xyz() const { return tvec3<T>(x, y, z); }
     tvec3<T> rgb() const { return tvec3<T>(x, y, z); }
+    GLSL_VEC_OPS(tvec4, 4)
 };
 
 typedef tvec2<float> vec2;   typedef tvec3<float> vec3;   typedef tvec4<float> vec4;
 typedef tvec2<int> ivec2;    typedef tvec3<int> ivec3;    typedef tvec4<int> ivec4;
 typedef tvec3<uint> uvec3;   typedef tvec4<uint> uvec4;
 typedef tvec3<bool> bvec3;
+
+// Column-major 4x4 matrix.  mat4 * vec4 accumulates the columns in order 0,1,2,3, one rounding per
+// product and per sum (D11).
+struct mat4 {
+    vec4 col[4];
+    friend vec4 operator*(const mat4& m, vec4 v) { return ((m.col[0] * v.x + m.col[1] * v.y) + m.col[2] * v.z) + m.col[3] * v.w; }
+};
 
 // GL_EXT_shader_explicit_arithmetic_types i8vec4, as the request SSBO stores it (radiance.comp:23-25)
 struct i8vec4 {
@@ -163,6 +173,8 @@ struct sampler3D {           // radiance field A2B10G10R10, LINEAR + REPEAT, nor
 struct image3D {
     uint32_t* data = nullptr; ivec3 size;
 };
+struct iimage3D { const int16_t* data = nullptr; ivec3 size; };      // r16i world grid (map.comp:16)
+struct uimage3D { uint8_t* data = nullptr; ivec3 size; };            // r8ui palette atlas / model voxels
 inline bool inside(ivec3 p, ivec3 s) { return p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < s.x && p.y < s.y && p.z < s.z; }
 inline ivec4 texelFetch(const isampler3D& t, ivec3 p, int) {
     t.fetches++;
@@ -210,6 +222,20 @@ inline vec4 textureLod(const sampler3D& t, vec3 uvw, float) {
 inline void imageStore(image3D& img, ivec3 p, vec4 c) {
     if (!inside(p, img.size)) return;
     img.data[p.x + (int64_t)img.size.x * (p.y + (int64_t)img.size.y * p.z)] = pack_rgb10a2(c);
+}
+
+inline ivec3 imageSize(const uimage3D& t) { return t.size; }
+inline ivec4 imageLoad(const iimage3D& t, ivec3 p) {                  // out of range -> 0 (D2)
+    if (!inside(p, t.size)) return ivec4(0, 0, 0, 0);
+    return ivec4(t.data[p.x + (int64_t)t.size.x * (p.y + (int64_t)t.size.y * p.z)], 0, 0, 1);
+}
+inline uvec4 imageLoad(const uimage3D& t, ivec3 p) {
+    if (!inside(p, t.size)) return uvec4(0, 0, 0, 0);
+    return uvec4(t.data[p.x + (int64_t)t.size.x * (p.y + (int64_t)t.size.y * p.z)], 0, 0, 1);
+}
+inline void imageStore(uimage3D& t, ivec3 p, uvec4 c) {
+    if (!inside(p, t.size)) return;
+    t.data[p.x + (int64_t)t.size.x * (p.y + (int64_t)t.size.y * p.z)] = (uint8_t)c.x;
 }
 
 // ---- per-invocation built-ins and the subgroup model ----

@@ -1,8 +1,10 @@
 /*
  * lum_oracle.c -- CPU restatement (ORACLE) of Lum's radiance-probe update path.
  *
- * TEST INFRASTRUCTURE ONLY (see lum_oracle.h).  PARITY UNPINNED: the reference has no
- * tests or golden vectors for this path and its GLSL cannot be executed here.
+ * TEST INFRASTRUCTURE ONLY (see lum_oracle.h).  PARITY PINNED AGAINST THE REFERENCE'S OWN
+ * SHADER TEXT, executed on the CPU (oracle/_ref/libref_radiance_glsl.so, recipe in
+ * oracle/Makefile): tests/test_ref_glsl.py and tests/golden/ref_glsl_golden.npz.  Driver-defined
+ * semantics (filter arithmetic, subgroup sum order, ...) remain decrees -- see lum_oracle.h.
  *
  * Every function follows the statement order of the reference text it cites
  * (paths relative to /root/reference).  Arithmetic rules pinned by decree

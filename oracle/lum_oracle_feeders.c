@@ -2,8 +2,10 @@
  * lum_oracle_feeders.c -- CPU restatement (ORACLE) of the feeders of Lum's radiance pass:
  * model placement, blockify, the brick copies of exec_copies, and shaders/map.comp.
  *
- * TEST INFRASTRUCTURE ONLY (see lum_oracle.h).  PARITY UNPINNED: the reference has no tests or
- * golden vectors for these functions and its GLSL / Vulkan host code cannot be executed here.
+ * TEST INFRASTRUCTURE ONLY (see lum_oracle.h).  map.comp is PINNED against the reference's own
+ * shader text executed on the CPU (oracle/_ref/libref_map_glsl.so, tests/test_ref_glsl.py);
+ * placement / blockify / copies are PARITY UNPINNED: the reference has no tests or golden vectors
+ * for them and its Vulkan host code (internal_render.cpp) does not compile from a few sources.
  * Each function follows the statement order of the reference text it cites (paths relative to
  * /root/reference).  Arithmetic rules: as lum_oracle.c (binary32/binary64 exactly as the reference
  * types them, one rounding per written operation, no FMA contraction).

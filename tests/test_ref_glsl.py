@@ -110,3 +110,62 @@ def test_oracle_matches_live_reference_shader_edge_world(oracle_mod):
         assert np.array_equal(2 + r["ray_coarse"].astype(np.int64) + r["ray_samples"], ref["ray_fetches"]), frame
         f = ref["field"]
     assert np.count_nonzero(f & 0x3FFFFFFF) > 0
+
+
+# ---- map.comp (feeder f1): the reference's own shader against the restatement ------------------
+needs_ref_map = pytest.mark.skipif(not __import__("oracle").ref_map_available(),
+                                   reason="oracle/_ref not built (needs /root/reference)")
+
+
+def _quat(axis, a):
+    ax = np.asarray(axis, np.float64); ax = ax / np.linalg.norm(ax)
+    s = np.sin(a / 2)
+    return tuple(np.float32(v) for v in (np.cos(a / 2), ax[0] * s, ax[1] * s, ax[2] * s))
+
+
+@needs_ref_map
+def test_map_oracle_matches_reference_shader(oracle_mod, demo):
+    """Config-3 style placements (tank and robot models, yawed/tilted, partly outside the high
+    world faces): bricks after blockify + copies + map are byte-equal."""
+    O = oracle_mod
+    ws = (48, 48, 16)
+    cases = [("model_tank_body", _quat((0, 0, 1), 0.0), (13.1 * 16, 14.1 * 16, 3.1 * 16)),
+             ("model_tank_head", _quat((0, 0, 1), 0.35), (13.1 * 16 + 6, 14.1 * 16 + 4, 3.1 * 16 + 9)),
+             ("model_robot", _quat((0, 0, 1), -2.1), (25.0, 30.0, 30.0)),
+             ("model_robot", _quat((1, 2, 3), 0.9), (300.5, 310.25, 60.0)),
+             ("model_tank", _quat((0, 1, 0), 0.2), (700.0, 705.0, 200.0)),
+             ("model_robot", (np.float32(0.5),) * 4, (740.0, 750.0, 240.0))]
+    total = 0
+    for name, rot, shift in cases:
+        if name not in demo:
+            continue
+        model = demo[name]
+        sz, sy, sx = model.shape
+        p = O.place_model(rot, shift, (sx, sy, sz), ws)
+        cur, src, dst = O.blockify(demo["world"], 15, [p])
+        bricks = np.zeros((512, 16, 16, 16), np.uint8)
+        bricks[:15] = demo["bricks"]
+        O.copy_bricks(bricks, src, dst)
+        ref = bricks.copy()
+        O.map_model(cur, bricks, model, p, 15)
+        O.ref_glsl_map_model(cur, ref, model, p)
+        assert np.array_equal(bricks, ref), name
+        total += int(np.count_nonzero(bricks[15:]))
+    assert total > 1000
+
+
+@needs_ref_map
+def test_map_two_models_in_draw_order(oracle_mod, demo):
+    O = oracle_mod
+    ws = (48, 48, 16)
+    a = O.place_model(_quat((0, 0, 1), 0.1), (13.1 * 16, 14.1 * 16, 3.1 * 16), demo["model_tank_body"].shape[::-1], ws)
+    b = O.place_model(_quat((0, 0, 1), 0.6), (13.3 * 16, 14.2 * 16, 3.4 * 16), demo["model_tank_head"].shape[::-1], ws)
+    cur, src, dst = O.blockify(demo["world"], 15, [a, b])
+    bricks = np.zeros((256, 16, 16, 16), np.uint8)
+    bricks[:15] = demo["bricks"]
+    O.copy_bricks(bricks, src, dst)
+    ref = bricks.copy()
+    for m, p in ((demo["model_tank_body"], a), (demo["model_tank_head"], b)):
+        O.map_model(cur, bricks, m, p, 15)
+        O.ref_glsl_map_model(cur, ref, m, p)
+    assert np.array_equal(bricks, ref)
