@@ -102,6 +102,9 @@ struct LumcuCtx {
     int carveout = -1;
     int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
     bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
+    uint32_t *d_scene_flags = nullptr;     // bit 0: world ids outside the palette (validate_world_kernel)
+    bool world_dirty = true;     // the world changed since the last validation
+    bool world_shared = false;   // its device address was handed out: validate before every update
 
     // builder scratch (lazy)
     uint8_t *d_flags = nullptr;
@@ -175,9 +178,10 @@ void host_direction_table(int n, std::vector<float> &out) {
     }
 }
 
-// production path: pooled kernel (no z filter); one CTA per 4*threads rays
+// production path: pooled kernel (no z filter); one CTA per RPT*threads rays
 #ifndef LUMCU_RPT
-#define LUMCU_RPT 4           // rays per thread of the reference-shaped (R = 64) production kernel
+#define LUMCU_RPT 3           // rays per thread of the reference-shaped (R = 64) production kernel: 384 rays = 6 probes
+                              // per CTA, 16 KB of ray slots (B200, C4 world: 22.16 ms; RPT 4: 23.16, RPT 2: 24.15)
 #endif
 template <int R, int T, int RPT, bool DEBUG>
 int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
@@ -196,8 +200,12 @@ int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, lo
     switch (c->R) {
         case 16: return launch_pool_one<16, 256, 4, DEBUG>(c, sv, a, nwg);
         case 32: return launch_pool_one<32, 256, 4, DEBUG>(c, sv, a, nwg);
+#ifdef LUMCU_T64
+        case 64: return launch_pool_one<64, 64, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
+#else
         case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg)
                                                : launch_pool_one<64, 256, 4, DEBUG>(c, sv, a, nwg);
+#endif
         case 128: return launch_pool_one<128, 256, 4, DEBUG>(c, sv, a, nwg);
         case 256: return launch_pool_one<256, 256, 4, DEBUG>(c, sv, a, nwg);
         default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);
@@ -244,7 +252,17 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         return fail(LUMCU_E_ARG, "workgroup range [%lld,%lld) outside [0,%lld)", wg_begin, wg_end, nwg_all);
     const long long nwg = wg_end - wg_begin;
     if (nwg > 0) {
-        SceneView sv{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity, c->brick0_empty ? 1 : 0};
+        if (c->world_dirty || c->world_shared) {
+            CU(cudaMemsetAsync(c->d_scene_flags, 0, sizeof(uint32_t), c->stream));
+            const int vt = 256;
+            const long long vb = std::min<long long>((c->cells + vt - 1) / vt, 148 * 8);
+            validate_world_kernel<<<(unsigned)vb, vt, 0, c->stream>>>(c->d_world, c->cells, c->desc.palette_capacity, c->d_scene_flags);
+            c->launches++;
+            CU(cudaGetLastError());
+            c->world_dirty = false;
+        }
+        SceneView sv{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
+                     c->brick0_empty ? 1 : 0, c->d_scene_flags};
         UpdateArgs a{};
         a.requests = c->d_requests;
         a.dir_table = c->d_table;
@@ -347,6 +365,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaEventCreate(&c->ev_k0));
     CUB(cudaEventCreate(&c->ev_k1));
     CUB(cudaMalloc(&c->d_world, (size_t)c->cells * sizeof(int16_t)));
+    CUB(cudaMalloc(&c->d_scene_flags, sizeof(uint32_t)));
     CUB(cudaMalloc(&c->d_bricks, (size_t)d->palette_capacity * 4096));
     CUB(cudaMalloc(&c->d_materials, 256 * 6 * sizeof(float)));
     CUB(cudaMalloc(&c->d_field, (size_t)c->cells * sizeof(uint32_t)));
@@ -377,6 +396,7 @@ int lumcu_destroy(LumcuCtx *c) {
     if (!c) return 0;
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_scene_flags);
     cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_field);
     cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
     cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
@@ -428,6 +448,7 @@ int lumcu_upload_world(LumcuCtx *c, const int16_t *world) {
     if (!world) return fail(LUMCU_E_ARG, "null world");
     if (int rc = staged_upload(c, c->stage_world, c->d_world, world, (size_t)c->cells * sizeof(int16_t))) return rc;
     c->have_world = true;
+    c->world_dirty = true;
     return 0;
 }
 
@@ -903,6 +924,7 @@ int lumcu_field_device_ptr(LumcuCtx *c, uint64_t *p) {
 int lumcu_world_device_ptr(LumcuCtx *c, uint64_t *p) {
     if (!c || !p) return fail(LUMCU_E_ARG, "null argument");
     *p = (uint64_t)(uintptr_t)c->d_world;
+    c->world_shared = true;      // the holder may write ids: the march revalidates before every update
     return 0;
 }
 int lumcu_stream(LumcuCtx *c, uint64_t *s) {

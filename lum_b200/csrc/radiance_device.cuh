@@ -21,6 +21,7 @@ struct SceneView {
     int wx, wy, wz;
     int capacity;                           // bricks addressable
     int brick0_empty;                       // brick 0 is all zeros (always, unless the user loaded a block 0)
+    const uint32_t *__restrict__ flags;     // bit 0: the world holds ids outside [0, capacity) (validate_world_kernel)
 };
 
 struct f3 { float x, y, z; };
@@ -161,7 +162,64 @@ __device__ __forceinline__ int march_step(const SceneView &s, const MarchConsts 
     const float tn = t + gmax(gmin(ex, gmin(ey, ez)), 0.01f);
     t = (id == 0) ? tn : t;
     const bool out = p.x < 0.0f || p.y < 0.0f || p.z < 0.0f || p.x >= mc.wsx || p.y >= mc.wsy || p.z >= mc.wsz;
-    return voxel != 0 ? 1 : ((out || t >= 128.0f) ? 2 : 0);
+    return voxel != 0 ? 1 : ((out || !(t < 128.0f)) ? 2 : 0);   // !(t<128): a NaN fraction ends the ray (decree 13)
+}
+
+// ---- the same iteration for the validated device mirror -----------------------------------
+// Preconditions (checked on the device, see SceneView::flags): brick 0 is empty and every world id is
+// in [0, capacity).  Differences from march_step, none of which can change a result:
+//   * `out` first, as ONE unsigned compare per axis on the float bits: negative floats compare above
+//     every positive bound, and pos is never -0.0 or NaN here (origin + dir*t with a finite t and an
+//     origin that is a sum with a non-zero first term), so this is exactly pos<0 || pos>=16*world_size;
+//   * an `out` lane does not fetch: it ends as "pending" and the one sample the reference still takes
+//     there (trunc-division aliases pos in (-1,0) onto voxel row 0) is taken by
+//     resolve_pending() in the shading phase, with the general get_voxel;
+//   * in-world lanes need no bounds test, no negative-coordinate division and no capacity test;
+//   * the cell corner float(16*b + {0,16}) is formed on the FMA pipe: bits = 0x4B000000 + 16*b + off is the
+//     float 2^23 + corner, minus 2^23 is exact.  cm.* = 0x4B000000 + (dir > 0 ? 16 : 0), per ray.
+// The loop of the pooled kernel is bound by the ALU pipe (ncu: 65 % of its peak, every other pipe < 25 %),
+// so the integer work is written as multiply-adds (IMAD, FMA-heavy pipe) wherever that is exact.
+// t_pre = the fraction at which pos was sampled (what a pending lane stores).
+__device__ __forceinline__ bool march_step_fast(const SceneView &s, const uint3 &wsbits, const f3 &o, const f3 &d,
+                                                const f3 &inv, const i3 &cm, float &t, float &t_pre, bool &hit) {
+    t += 0.5f;
+    t_pre = t;
+    const float px = o.x + d.x * t, py = o.y + d.y * t, pz = o.z + d.z * t;
+    const bool out = __float_as_uint(px) >= wsbits.x || __float_as_uint(py) >= wsbits.y || __float_as_uint(pz) >= wsbits.z;
+    const int ix = f2i(px), iy = f2i(py), iz = f2i(pz);
+    const int bx = ix >> 4, by = iy >> 4, bz = iz >> 4;
+    // Addresses are formed by every lane and only the loads are predicated (no divergent branch in the loop).
+    const int16_t *wp = s.world + (bx + s.wx * (by + s.wy * bz));
+    int id = 0;
+    if (!out) id = __ldg(wp);
+    // ((ix&15)<<8 | (iy&15)<<4 | iz&15) == V - 16*B with V = (ix*16+iy)*16+iz, B = (bx*16+by)*16+bz
+    const int V = (ix * 16 + iy) * 16 + iz, B = (bx * 16 + by) * 16 + bz;
+    const uint8_t *bp = s.bricks + (uint32_t)(id * 4096 + (V - 16 * B));
+    int voxel = 0;
+    if (id != 0) voxel = __ldg(bp);
+    const float cx = __int_as_float(bx * 16 + cm.x) - 8388608.0f;
+    const float cy = __int_as_float(by * 16 + cm.y) - 8388608.0f;
+    const float cz = __int_as_float(bz * 16 + cm.z) - 8388608.0f;
+    const float ex = cx * inv.x + (-px * inv.x);
+    const float ey = cy * inv.y + (-py * inv.y);
+    const float ez = cz * inv.z + (-pz * inv.z);
+    const float tn = t + gmax(gmin(ex, gmin(ey, ez)), 0.01f);
+    t = (id == 0) ? tn : t;
+    hit = voxel != 0;
+    return hit || out || !(t < 128.0f);
+}
+
+// A ray that ended without an in-world hit stored -t_pre.  If its last position was outside the world the
+// reference still sampled there before the bounds test (radiance.comp:212-237): take that one sample with
+// the general get_voxel.  Returns true if it hit after all; the fraction is then t_pre itself (brick 0 is
+// empty under the fast path's precondition, so a solid voxel implies block id != 0, i.e. no skip was added).
+__device__ __forceinline__ bool resolve_pending(const SceneView &s, const MarchConsts &mc, const f3 &o, const f3 &d,
+                                                float t_pre) {
+    const float px = o.x + d.x * t_pre, py = o.y + d.y * t_pre, pz = o.z + d.z * t_pre;
+    const bool out = px < 0.0f || py < 0.0f || pz < 0.0f || px >= mc.wsx || py >= mc.wsy || pz >= mc.wsz;
+    if (!out) return false;                 // in-world sample: the march already saw voxel == 0
+    int id;
+    return get_voxel(s, f2i(px), f2i(py), f2i(pz), id) != 0;
 }
 
 // ---- after the march: refinement + hit shading, or sky (radiance.comp:246-288,316-347) ----

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
 }
 
 // ---- pooled kernel: the production path ---------------------------------------------------
-// One CTA owns a batch of NR = 4*THREADS rays (NR/R probes) staged in shared memory:
+// One CTA owns a batch of NR = RPT*THREADS rays (NR/R probes) staged in shared memory:
 //   A  ray setup, one ray per thread per round, fully convergent.
 //   B  coarse march with lane-level dynamic refill from the CTA's ray pool: a lane whose ray
 //      ended immediately takes the next ray, so warps stay ~90 % full although ray lengths vary
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
 //      store_probe; one warp per probe.
 // The result does not depend on the schedule: each ray's sample sequence is a function of its
 // own (o, d, t) only, and the reduction tree is fixed.
-struct PoolRay { f3 o, d, inv; float t; int ns; };
+struct PoolRay { f3 o, d, inv; float t; int ns; i3 cm; };
 
 // Ray slots, packed for 16-byte shared-memory accesses: a = (o.xyz, t), b = (d.xyz, inv.x),
 // c = (inv.yz).  A refill is 2 x LDS.128 + 1 x LDS.64 instead of ten scalar loads; consecutive slots
@@ -111,7 +111,7 @@ struct PoolShared {
     float4 a[NR];
     float4 b[NR];
     float2 c[NR];
-    unsigned char done[NR];               // 1 = terminated during pass 0 (shaded by the chunk loop)
+    unsigned char done[NR];               // 1 = terminated during pass 0 (shaded by the chunk loop); 0 = was parked
     unsigned short ns[DEBUG ? NR : 1];    // marching samples so far (instrumented variant only)
     __device__ __forceinline__ void load(int r, PoolRay &q) const {
         const float4 va = a[r], vb = b[r];
@@ -121,6 +121,9 @@ struct PoolShared {
         q.inv = {vb.w, vc.x, vc.y};
         q.t = va.w;
         if constexpr (DEBUG) q.ns = ns[r];
+        // march_step_fast's per-ray corner constants: float bits of 2^23 + (dir > 0 ? 16 : 0)
+        q.cm = {0x4B000000 + (q.d.x > 0.0f ? 16 : 0), 0x4B000000 + (q.d.y > 0.0f ? 16 : 0),
+                0x4B000000 + (q.d.z > 0.0f ? 16 : 0)};
     }
 };
 
@@ -130,14 +133,16 @@ struct PoolShared {
 // PRIVATE: the warp owns positions [first, limit) outright (pass 0: each warp marches its own slice of
 // the batch, so a refill needs no shared counter, no atomic and no broadcast -- measured 2 % faster
 // than the CTA-wide pool; the stragglers are balanced across warps by the tail passes anyway).
-template <int NR, int PARK, bool DEBUG, bool PRIVATE>
+// FAST: march_step_fast (validated scene); a ray that ends without a hit stores -t_pre ("pending", see
+// resolve_pending), otherwise -t.
+template <int NR, int PARK, bool DEBUG, bool PRIVATE, bool FAST>
 __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const SceneView &s, const MarchConsts &mc,
                                            int *next, int first, const unsigned short *src, int limit,
-                                           unsigned short *dst, int *dst_count, bool can_park, bool mark_done,
-                                           int lane) {
+                                           unsigned short *dst, int *dst_count, bool can_park, int lane) {
     constexpr unsigned FULL = 0xffffffffu;
+    const uint3 wsbits = {__float_as_uint(mc.wsx), __float_as_uint(mc.wsy), __float_as_uint(mc.wsz)};
     int cur = -1;
-    PoolRay q = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, 0.0f, 0};
+    PoolRay q = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, 0.0f, 0, {0, 0, 0}};
     bool exhausted = false;
     int mine = first;                                              // PRIVATE: next unclaimed position
     for (;;) {
@@ -172,6 +177,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                     if (cur >= 0) {
                         dst[base + __popc(~idle & ((1u << lane) - 1u))] = (unsigned short)cur;
                         sm.a[cur].w = q.t;
+                        sm.done[cur] = 0;
                         if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                     }
                     break;
@@ -179,11 +185,18 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
             }
         }
         if (cur >= 0) {
-            const int st = march_step(s, mc, q.o, q.d, q.inv, q.t);
+            bool done, hit;
+            float t_end;                                            // what a ray that ends without a hit stores
+            if constexpr (FAST) {
+                done = march_step_fast(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit);
+            } else {
+                const int st = march_step(s, mc, q.o, q.d, q.inv, q.t);
+                done = st != 0; hit = st == 1;
+                t_end = q.t;
+            }
             q.ns++;
-            if (st) {
-                sm.a[cur].w = st == 1 ? q.t : -q.t;                // sign = miss (t >= 0.5 always)
-                if (mark_done) sm.done[cur] = 1;
+            if (done) {
+                sm.a[cur].w = hit ? q.t : -t_end;                  // sign = no hit (t >= 0.5 always)
                 if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                 cur = -1;
             }
@@ -192,13 +205,14 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
 }
 
 // Refinement + shading of slot r; the slot's o[] is replaced by the ray's light.
-template <int NR, int R, bool DEBUG>
-__device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const SceneView &s, const UpdateArgs &a,
-                                           long long wg0, int r, f3 sun, unsigned long long &my_s,
-                                           unsigned long long &my_h) {
+template <int NR, int R, bool DEBUG, bool FAST>
+__device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const SceneView &s, const MarchConsts &mc,
+                                           const UpdateArgs &a, long long wg0, int r, f3 sun,
+                                           unsigned long long &my_s, unsigned long long &my_h) {
     PoolRay q;
     sm.load(r, q);
-    const bool hit = q.t > 0.0f;
+    bool hit = q.t > 0.0f;
+    if constexpr (FAST) { if (!hit) hit = resolve_pending(s, mc, q.o, q.d, -q.t); }
     int nr;
     const f3 l = finish_ray(s, q.o, q.d, q.inv, fabsf(q.t), hit, sun, nr);
     sm.a[r].x = l.x; sm.a[r].y = l.y; sm.a[r].z = l.z;
@@ -210,25 +224,35 @@ __device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const Scen
     }
 }
 
-template <int R, int THREADS, int RPT, bool DEBUG>
-__global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView s, UpdateArgs a) {
-    constexpr int NR = RPT * THREADS;        // rays per batch (RPT rays per thread)
-    constexpr int PPC = NR / R;              // probes per CTA
-    constexpr int NW = THREADS / 32;
 #ifndef LUMCU_PARK
 #define LUMCU_PARK 8          // tuned on B200 (C4 world): 8 beats 1/4/16/24/32
 #endif
-    constexpr int PARK = LUMCU_PARK;
-    constexpr int LIST = NW * PARK;
+template <int R, int THREADS, int RPT, bool DEBUG>
+struct PoolCta {
+    static constexpr int NR = RPT * THREADS;        // rays per batch (RPT rays per thread)
+    static constexpr int PPC = NR / R;              // probes per CTA
+    static constexpr int NW = THREADS / 32;
+    static constexpr int PARK = LUMCU_PARK;
+    static constexpr int LIST = NW * PARK;
+    static_assert(PPC >= 1, "batch smaller than one probe");
+    PoolShared<NR, DEBUG> sm;
+    unsigned short list[3][LIST];   // [0] = stragglers of pass 0, [1],[2] ping-pong afterwards
+    short4 req[PPC];
+    int next, park[3], chunk;
+};
+
+template <int R, int THREADS, int RPT, bool DEBUG, bool FAST>
+__device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &cta, const SceneView &s, const UpdateArgs &a) {
+    using Cta = PoolCta<R, THREADS, RPT, DEBUG>;
+    constexpr int NR = Cta::NR, PPC = Cta::PPC, NW = Cta::NW, PARK = Cta::PARK;
     constexpr int SUB = R < 32 ? R : 32;
     constexpr int NSUB = R / SUB;
     constexpr unsigned FULL = 0xffffffffu;
-    static_assert(PPC >= 1, "batch smaller than one probe");
-    __shared__ PoolShared<NR, DEBUG> sm;
-    __shared__ unsigned short sm_list[3][LIST];   // [0] = stragglers of pass 0, [1],[2] ping-pong afterwards
-    __shared__ short4 sm_req[PPC];
-    __shared__ int sm_next, sm_park[3], sm_chunk;
-
+    PoolShared<NR, DEBUG> &sm = cta.sm;
+    unsigned short (&sm_list)[3][Cta::LIST] = cta.list;
+    short4 (&sm_req)[PPC] = cta.req;
+    int &sm_next = cta.next, &sm_chunk = cta.chunk;
+    int (&sm_park)[3] = cta.park;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long wg0 = a.wg_begin + (long long)blockIdx.x * PPC;
     const long long left = a.wg_end - wg0;
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
         sm.a[r] = make_float4(o.x, o.y, o.z, 0.0f);
         sm.b[r] = make_float4(d.x, d.y, d.z, inv.x);
         sm.c[r] = make_float2(inv.y, inv.z);
-        sm.done[r] = 0;
+        sm.done[r] = 1;
         if constexpr (DEBUG) sm.ns[r] = 0;
     }
     __syncthreads();
@@ -258,7 +282,7 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
     const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
     {   // warp w owns slots [w*NR/NW, (w+1)*NR/NW) of the batch
         const int first = warp * (NR / NW), last = min(nrays, first + NR / NW);
-        pool_march<NR, PARK, DEBUG, true>(sm, s, mc, nullptr, first, nullptr, last, sm_list[0], &sm_park[0], NW > 1, true, lane);
+        pool_march<NR, PARK, DEBUG, true, FAST>(sm, s, mc, nullptr, first, nullptr, last, sm_list[0], &sm_park[0], NW > 1, lane);
     }
     __syncthreads();
     const int parked0 = sm_park[0];
@@ -274,7 +298,7 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
             asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
             const int parts = max(1, min(tail_warps, (limit + 47) / 48));
             if (warp < parts)
-                pool_march<NR, PARK, DEBUG, false>(sm, s, mc, &sm_next, 0, sm_list[rd], limit, sm_list[wr], &sm_park[wr], parts > 1, false, lane);
+                pool_march<NR, PARK, DEBUG, false, FAST>(sm, s, mc, &sm_next, 0, sm_list[rd], limit, sm_list[wr], &sm_park[wr], parts > 1, lane);
             asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
             const int parked = sm_park[wr];
             if (parked == 0) break;
@@ -292,11 +316,11 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
         c = __shfl_sync(FULL, c, 0);
         if (c >= nrays) break;
         const int r = c + lane;
-        if (r < nrays && sm.done[r]) pool_shade<NR, R, DEBUG>(sm, s, a, wg0, r, sun, my_s, my_h);
+        if (r < nrays && sm.done[r]) pool_shade<NR, R, DEBUG, FAST>(sm, s, mc, a, wg0, r, sun, my_s, my_h);
     }
     if (warp < tail_warps)                                 // the stragglers, now finished too
         for (int i = tid; i < parked0; i += tail_threads)
-            pool_shade<NR, R, DEBUG>(sm, s, a, wg0, sm_list[0][i], sun, my_s, my_h);
+            pool_shade<NR, R, DEBUG, FAST>(sm, s, mc, a, wg0, sm_list[0][i], sun, my_s, my_h);
     if constexpr (DEBUG) {
 #pragma unroll
         for (int k = 16; k >= 1; k >>= 1) {
@@ -342,6 +366,32 @@ __global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView
             a.staged[w] = word;
         }
     }
+}
+
+
+#ifdef LUMCU_MINB             // tuning knob: min resident CTAs per SM asked of ptxas (a register cap)
+#define LUMCU_POOL_BOUNDS __launch_bounds__(THREADS, LUMCU_MINB)
+#else
+#define LUMCU_POOL_BOUNDS __launch_bounds__(THREADS)
+#endif
+template <int R, int THREADS, int RPT, bool DEBUG>
+__global__ void LUMCU_POOL_BOUNDS radiance_update_pool_kernel(SceneView s, UpdateArgs a) {
+    __shared__ PoolCta<R, THREADS, RPT, DEBUG> cta;
+    // The fast march needs brick 0 empty and every world id inside the palette; the second is a property of
+    // the uploaded data, checked on the device (validate_world_kernel) so that no host sync is needed.
+    const bool general = !s.brick0_empty || (__ldg(s.flags) & 1u);
+    if (general) pool_cta_body<R, THREADS, RPT, DEBUG, false>(cta, s, a);
+    else pool_cta_body<R, THREADS, RPT, DEBUG, true>(cta, s, a);
+}
+
+// bit 0 of *flags: some world id lies outside [0, capacity) (such a block marches as "non-empty, all voxels
+// empty", radiance_device.cuh get_voxel).  *flags is zeroed before the launch.
+__global__ void validate_world_kernel(const int16_t *__restrict__ world, long long cells, int capacity,
+                                      uint32_t *__restrict__ flags) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x)
+        bad |= (unsigned)world[i] >= (unsigned)capacity;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1u);
 }
 
 // Deferred imageStore (radiance.comp:353): scatter the staged texels of workgroups

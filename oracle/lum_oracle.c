@@ -190,7 +190,7 @@ static int cast_ray_fast(const LumOracleScene *s, v3 origin, v3 dir,
         if (voxel != 0) break;                                           /* :228-231 */
         if (pos.x < 0.0f || pos.y < 0.0f || pos.z < 0.0f ||              /* :233-237 */
             pos.x >= wsx || pos.y >= wsy || pos.z >= wsz) break;
-        if (fraction >= max_dist) break;                                 /* :239-243 */
+        if (!(fraction < max_dist)) break;                               /* :239-243; NaN-safe form (decree 13): a NaN fraction ends the ray instead of looping forever */
     }
     *coarse_samples = ns;
     *refine_samples = 0;

@@ -231,6 +231,57 @@ def test_solid_world_and_saturation(oracle_mod):
     assert np.all(ref["field"] == 0xFFFFFFFF)
 
 
+def test_boundary_shell_hits_after_leaving(oracle_mod):
+    """The sample the reference takes at pos in (-1,0) aliases onto voxel row 0 of the edge block
+    (SURVEY a6).  Edge bricks here are solid only in their outermost voxel rows, so the rays that leave
+    through a low face hit exactly through that aliased sample (the fast march's "pending" lanes)."""
+    O = oracle_mod
+    rng = np.random.default_rng(5)
+    shell = np.zeros((16, 16, 16), np.uint8)        # [x][y][z]
+    shell[0, :, :] = 3; shell[:, 0, :] = 4; shell[:, :, 0] = 5
+    mats = rng.random((256, 6)).astype(np.float32)
+    bricks = np.stack([np.zeros_like(shell), shell, np.zeros_like(shell)])
+    world = np.zeros((3, 4, 5), np.int16)            # [z][y][x]
+    world[0, :, :] = 1; world[:, 0, :] = 1; world[:, :, 0] = 1
+    world[2, 3, 4] = 2                               # a non-empty block whose brick is all empty voxels
+    scn = dict(world=world, bricks=bricks, materials=mats)
+    st = make_stage(scn)
+    sc = oracle_scene(O, scn)
+    req = np.array([(x, y, z, 0) for z in range(3) for y in range(4) for x in range(5)], np.int16)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    for seed in (0, 3, 11):
+        ref = assert_update_equal(st, O, sc, f0, req, seed)
+    assert 0 < ref["totals"][1] < len(req) * 64
+
+
+@pytest.mark.parametrize("case", ["ids_outside_palette", "brick0_loaded"])
+def test_general_march_path(oracle_mod, small_synth, case):
+    """The pooled kernel's fast march requires brick 0 empty and every world id inside the palette; both are
+    detected (host flag / validate_world_kernel) and such scenes take the general march."""
+    O = oracle_mod
+    scn = {k: v.copy() for k, v in small_synth.items()}
+    rng = np.random.default_rng(17)
+    if case == "ids_outside_palette":
+        flat = scn["world"].reshape(-1)
+        idx = rng.choice(flat.size, 40, replace=False)
+        flat[idx[:20]] = -7                          # negative and beyond-capacity ids: "non-empty, no voxels"
+        flat[idx[20:]] = scn["bricks"].shape[0] + 5
+    else:
+        scn["bricks"][0] = (rng.random((16, 16, 16)) < 0.02) * 9
+    st = make_stage(scn)
+    sc = oracle_scene(O, scn)
+    req = O.build_requests(scn["world"])
+    if len(req) == 0 or case == "brick0_loaded":
+        wz, wy, wx = scn["world"].shape
+        req = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    assert_update_equal(st, O, sc, f0, req, 9)
+    # back to a valid world on the same stage: the flag is recomputed per upload
+    st.upload_world(small_synth["world"]); st.upload_bricks(0, small_synth["bricks"])
+    sc2 = oracle_scene(O, small_synth)
+    assert_update_equal(st, O, sc2, f0, O.build_requests(small_synth["world"]), 10)
+
+
 def test_ranges_and_slabs_compose(oracle_mod, demo):
     """Probe sharding: disjoint workgroup ranges / z-slabs reproduce the full update exactly."""
     O = oracle_mod
