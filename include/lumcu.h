@@ -200,6 +200,34 @@ int lumcu_last_kernel_ms(LumcuCtx *ctx, float *ms);
 /* Number of kernels this library launched on the context so far. */
 int lumcu_launch_count(LumcuCtx *ctx, uint64_t *count);
 
+/* ---- glossy reflections: shaders/glossy.frag as a CUDA pass -------------------
+ * The second consumer of the marcher: one mirror ray per G-buffer pixel through the same world /
+ * palette / materials, lit by the radiance field (glossy.frag:119-226 CastRay_fast, :328-360
+ * trace_glossy_ray, :439-491 main).  Replaces the fullscreen draw of LumInternalRenderer::glossy()
+ * (internal_render.cpp:2027-2037) and the stencil rule of fillStencilGlossy.frag (roughness <= 0.5).
+ * LumcuGlossyView mirrors the fields of the uniform block the shader reads (shaders/common/ubo.glsl,
+ * filled at internal_render.cpp:1580-1592). */
+typedef struct LumcuGlossyView {
+    float campos[3];              /* ubo.campos.xyz                                                */
+    float camdir[3];              /* ubo.camdir.xyz                                                */
+    float horizline_scaled[3];    /* camera.horizline * viewSize.x / 2                             */
+    float vertiline_scaled[3];    /* camera.vertiline * viewSize.y / 2                             */
+    float global_light_dir[3];    /* ubo.globalLightDir.xyz                                        */
+    float frame_size[2];          /* ubo.frame_size (swapchain extent)                             */
+} LumcuGlossyView;
+/* mat_norm: uint8 [height][width][4] = highresMatNorm, R8G8B8A8_UINT: material id, then the normal as
+ * (n+1)/2*255 (internal_render.hpp:455).  depth: float [height][width] = the depth attachment's value in
+ * [0,1] (the shader scales it by 1000).  frame: float [height][width][4], the fragment colour BEFORE the
+ * blend stage (rgb = light/8, a = 1 - roughness); only covered pixels are written.  covered (may be NULL):
+ * uint8 [height][width], 1 where the stencil rule lets the pass run.  Host buffers; the pass reads the
+ * field as it is on the stream (after the last update/commit). */
+int lumcu_glossy(LumcuCtx *ctx, const LumcuGlossyView *view, int32_t width, int32_t height,
+                 const uint8_t *mat_norm, const float *depth, float *frame, uint8_t *covered);
+/* Same with DEVICE buffers (interop with a renderer that keeps its G-buffer on the GPU); asynchronous on
+ * the context's stream. */
+int lumcu_glossy_device(LumcuCtx *ctx, const LumcuGlossyView *view, int32_t width, int32_t height,
+                        uint64_t mat_norm_dev, uint64_t depth_dev, uint64_t frame_dev, uint64_t covered_dev);
+
 /* Interop getters: raw device addresses and the stream (cudaStream_t) as integers. */
 int lumcu_field_device_ptr(LumcuCtx *ctx, uint64_t *ptr);
 int lumcu_world_device_ptr(LumcuCtx *ctx, uint64_t *ptr);

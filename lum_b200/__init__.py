@@ -30,6 +30,12 @@ class LumcuDesc(C.Structure):
                 ("device", C.c_int32), ("max_requests", C.c_int64)]
 
 
+class LumcuGlossyView(C.Structure):
+    _fields_ = [("campos", C.c_float * 3), ("camdir", C.c_float * 3), ("horizline_scaled", C.c_float * 3),
+                ("vertiline_scaled", C.c_float * 3), ("global_light_dir", C.c_float * 3),
+                ("frame_size", C.c_float * 2)]
+
+
 # every symbol include/lumcu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -72,6 +78,9 @@ SYMBOLS = {
     "lumcu_set_profiling": (C.c_int, [_P, C.c_int32]),
     "lumcu_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lumcu_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "lumcu_glossy": (C.c_int, [_P, C.POINTER(LumcuGlossyView), C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "lumcu_glossy_device": (C.c_int, [_P, C.POINTER(LumcuGlossyView), C.c_int32, C.c_int32,
+                                      C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "lumcu_field_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "lumcu_world_device_ptr": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "lumcu_stream": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
@@ -193,6 +202,28 @@ class RadianceStage:
     def update_slab_exchange(self, time_seed, size, shift, z_begin, z_end):
         self._ck(self.lib.lumcu_update_slab_exchange(self.ctx, int(time_seed), int(size), int(shift),
                                                      int(z_begin), int(z_end)))
+
+    # -- glossy reflections (glossy.frag) ----------------------------------------------------
+    @staticmethod
+    def glossy_view(view):
+        """dict(campos, camdir, horizline_scaled, vertiline_scaled, global_light_dir, frame_size) -> LumcuGlossyView"""
+        v = LumcuGlossyView()
+        for k in ("campos", "camdir", "horizline_scaled", "vertiline_scaled", "global_light_dir"):
+            getattr(v, k)[:] = [float(np.float32(x)) for x in view[k]]
+        v.frame_size[:] = [float(np.float32(x)) for x in view["frame_size"]]
+        return v
+
+    def glossy(self, view, mat_norm, depth, frame=None):
+        """mat_norm uint8 [h,w,4]; depth float32 [h,w]; returns (frame float32 [h,w,4], covered uint8 [h,w])."""
+        mn = np.ascontiguousarray(mat_norm, np.uint8)
+        h, w = mn.shape[:2]
+        dp = np.ascontiguousarray(depth, np.float32)
+        assert mn.shape == (h, w, 4) and dp.shape == (h, w)
+        fr = np.zeros((h, w, 4), np.float32) if frame is None else np.ascontiguousarray(frame, np.float32)
+        cov = np.zeros((h, w), np.uint8)
+        v = self.glossy_view(view)
+        self._ck(self.lib.lumcu_glossy(self.ctx, C.byref(v), w, h, _ptr(mn), _ptr(dp), _ptr(fr), _ptr(cov)))
+        return fr, cov
 
     def shift(self, dx, dy, dz):
         self._ck(self.lib.lumcu_shift(self.ctx, int(dx), int(dy), int(dz)))

@@ -145,6 +145,10 @@ struct LumcuCtx {
     unsigned *d_status = nullptr;
     unsigned epoch = 0;
 
+    // glossy pass scratch for the host-buffer entry point (lazy)
+    uchar4 *d_g_matnorm = nullptr; float *d_g_depth = nullptr; float4 *d_g_frame = nullptr; uint8_t *d_g_cov = nullptr;
+    long long g_cap = 0;
+
     Staging stage_world, stage_req, stage_misc, stage_pairs;
     uint64_t launches = 0;
 };
@@ -241,6 +245,25 @@ int ensure_debug(LumcuCtx *c) {
     return 0;
 }
 
+// Device-side check that every world id is inside the palette (what march_step_fast relies on); no host sync.
+int ensure_validated(LumcuCtx *c) {
+    if (c->world_dirty || c->world_shared) {
+        CU(cudaMemsetAsync(c->d_scene_flags, 0, sizeof(uint32_t), c->stream));
+        const int vt = 256;
+        const long long vb = std::min<long long>((c->cells + vt - 1) / vt, 148 * 8);
+        validate_world_kernel<<<(unsigned)vb, vt, 0, c->stream>>>(c->d_world, c->cells, c->desc.palette_capacity, c->d_scene_flags);
+        c->launches++;
+        CU(cudaGetLastError());
+        c->world_dirty = false;
+    }
+    return 0;
+}
+
+SceneView scene_view(LumcuCtx *c) {
+    return SceneView{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
+                     c->brick0_empty ? 1 : 0, c->d_scene_flags};
+}
+
 int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begin, long long wg_end,
               int z_begin, int z_end, bool commit = true) {
     if (!c->have_world || !c->have_bricks || !c->have_materials)
@@ -252,17 +275,8 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         return fail(LUMCU_E_ARG, "workgroup range [%lld,%lld) outside [0,%lld)", wg_begin, wg_end, nwg_all);
     const long long nwg = wg_end - wg_begin;
     if (nwg > 0) {
-        if (c->world_dirty || c->world_shared) {
-            CU(cudaMemsetAsync(c->d_scene_flags, 0, sizeof(uint32_t), c->stream));
-            const int vt = 256;
-            const long long vb = std::min<long long>((c->cells + vt - 1) / vt, 148 * 8);
-            validate_world_kernel<<<(unsigned)vb, vt, 0, c->stream>>>(c->d_world, c->cells, c->desc.palette_capacity, c->d_scene_flags);
-            c->launches++;
-            CU(cudaGetLastError());
-            c->world_dirty = false;
-        }
-        SceneView sv{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
-                     c->brick0_empty ? 1 : 0, c->d_scene_flags};
+        if (int rc = ensure_validated(c)) return rc;
+        const SceneView sv = scene_view(c);
         UpdateArgs a{};
         a.requests = c->d_requests;
         a.dir_table = c->d_table;
@@ -397,6 +411,7 @@ int lumcu_destroy(LumcuCtx *c) {
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_scene_flags);
+    cudaFree(c->d_g_matnorm); cudaFree(c->d_g_depth); cudaFree(c->d_g_frame); cudaFree(c->d_g_cov);
     cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_field);
     cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
     cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
@@ -913,6 +928,62 @@ int lumcu_last_kernel_ms(LumcuCtx *c, float *ms) {
 int lumcu_launch_count(LumcuCtx *c, uint64_t *count) {
     if (!c || !count) return fail(LUMCU_E_ARG, "null argument");
     *count = c->launches;
+    return 0;
+}
+
+int lumcu_glossy_device(LumcuCtx *c, const LumcuGlossyView *v, int32_t width, int32_t height,
+                        uint64_t mat_norm_dev, uint64_t depth_dev, uint64_t frame_dev, uint64_t covered_dev) {
+    if (int rc = use(c)) return rc;
+    if (!v || width < 1 || height < 1 || (long long)width * height > (1ll << 28))
+        return fail(LUMCU_E_ARG, "bad glossy frame (%d x %d)", width, height);
+    if (!mat_norm_dev || !depth_dev || !frame_dev) return fail(LUMCU_E_ARG, "null G-buffer / frame");
+    if (!c->have_world || !c->have_bricks || !c->have_materials)
+        return fail(LUMCU_E_STATE, "lumcu_glossy before world/bricks/materials were uploaded");
+    if (int rc = ensure_validated(c)) return rc;
+    GlossyArgs a{};
+    for (int k = 0; k < 3; k++) {
+        a.campos[k] = v->campos[k]; a.camdir[k] = v->camdir[k]; a.hs[k] = v->horizline_scaled[k];
+        a.vs[k] = v->vertiline_scaled[k]; a.gld[k] = v->global_light_dir[k];
+    }
+    a.fw = v->frame_size[0]; a.fh = v->frame_size[1];
+    a.width = width; a.height = height;
+    a.mat_norm = (const uchar4 *)(uintptr_t)mat_norm_dev;
+    a.depth = (const float *)(uintptr_t)depth_dev;
+    a.frame = (float4 *)(uintptr_t)frame_dev;
+    a.covered = (uint8_t *)(uintptr_t)covered_dev;
+    dim3 grid((unsigned)((width + 31) / 32), (unsigned)((height + 3) / 4));
+    glossy_kernel<<<grid, 128, 0, c->stream>>>(scene_view(c), a);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lumcu_glossy(LumcuCtx *c, const LumcuGlossyView *v, int32_t width, int32_t height,
+                 const uint8_t *mat_norm, const float *depth, float *frame, uint8_t *covered) {
+    if (int rc = use(c)) return rc;
+    if (!v || width < 1 || height < 1 || (long long)width * height > (1ll << 28))
+        return fail(LUMCU_E_ARG, "bad glossy frame (%d x %d)", width, height);
+    if (!mat_norm || !depth || !frame) return fail(LUMCU_E_ARG, "null G-buffer / frame");
+    const long long n = (long long)width * height;
+    if (c->g_cap < n) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_g_matnorm); cudaFree(c->d_g_depth); cudaFree(c->d_g_frame); cudaFree(c->d_g_cov);
+        c->d_g_matnorm = nullptr; c->d_g_depth = nullptr; c->d_g_frame = nullptr; c->d_g_cov = nullptr; c->g_cap = 0;
+        CU(cudaMalloc(&c->d_g_matnorm, (size_t)n * sizeof(uchar4)));
+        CU(cudaMalloc(&c->d_g_depth, (size_t)n * sizeof(float)));
+        CU(cudaMalloc(&c->d_g_frame, (size_t)n * sizeof(float4)));
+        CU(cudaMalloc(&c->d_g_cov, (size_t)n));
+        c->g_cap = n;
+    }
+    // caller buffers are read before the call returns: plain synchronous-with-respect-to-host copies
+    CU(cudaMemcpyAsync(c->d_g_matnorm, mat_norm, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_g_depth, depth, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_g_frame, frame, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = lumcu_glossy_device(c, v, width, height, (uint64_t)(uintptr_t)c->d_g_matnorm, (uint64_t)(uintptr_t)c->d_g_depth,
+                                     (uint64_t)(uintptr_t)c->d_g_frame, (uint64_t)(uintptr_t)c->d_g_cov)) return rc;
+    CU(cudaMemcpyAsync(frame, c->d_g_frame, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (covered) CU(cudaMemcpyAsync(covered, c->d_g_cov, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

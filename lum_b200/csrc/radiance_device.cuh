@@ -222,36 +222,47 @@ __device__ __forceinline__ bool resolve_pending(const SceneView &s, const MarchC
     return get_voxel(s, f2i(px), f2i(py), f2i(pz), id) != 0;
 }
 
+// ---- refinement after a coarse hit (radiance.comp:246-288 == glossy.frag:182-224) --------------
+// t = fraction at loop exit.  Outputs the face normal, the refined fraction and the material id;
+// refine_samples counts GetVoxel calls.
+__device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, const f3 &d, const f3 &inv, float t,
+                                           f3 &n, float &tf, int &vid, int &refine_samples) {
+    float tb = t - 1.5f;
+    f3 h = {o.x + d.x * tb, o.y + d.y * tb, o.z + d.z * tb};
+    int stx = d.x > 0.0f ? 1 : -1, sty = d.y > 0.0f ? 1 : -1, stz = d.z > 0.0f ? 1 : -1;
+    float c1x = (floorf(h.x) - h.x) / d.x, c1y = (floorf(h.y) - h.y) / d.y, c1z = (floorf(h.z) - h.z) / d.z;
+    f3 tMax = {gmax(c1x, c1x + inv.x), gmax(c1y, c1y + inv.y), gmax(c1z, c1z + inv.z)};
+    f3 tDelta = {fabsf(inv.x), fabsf(inv.y), fabsf(inv.z)};   // 1/|d| == |1/d| exactly
+    int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    int id;
+    vid = get_voxel(s, vx, vy, vz, id);
+    int ns = 1;
+    int it = 0;
+    while ((it++ <= 4) && (vid == 0)) {
+        ax = ((tMax.x <= tMax.y) && (tMax.x <= tMax.z)) ? 1.0f : 0.0f;
+        ay = ((tMax.x >= tMax.y) && (tMax.y <= tMax.z)) ? 1.0f : 0.0f;
+        az = ((tMax.z <= tMax.x) && (tMax.z <= tMax.y)) ? 1.0f : 0.0f;
+        vx += stx * (int)ax; vy += sty * (int)ay; vz += stz * (int)az;
+        tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
+        vid = get_voxel(s, vx, vy, vz, id);
+        ns++;
+    }
+    refine_samples = ns;
+    n = {-((float)stx * ax), -((float)sty * ay), -((float)stz * az)};
+    tf = (tMax.x - tDelta.x) * ax + (tMax.y - tDelta.y) * ay + (tMax.z - tDelta.z) * az;
+}
+
 // ---- after the march: refinement + hit shading, or sky (radiance.comp:246-288,316-347) ----
 // t = fraction at loop exit; hit = CastRay_fast's return value.  refine_samples counts GetVoxel calls.
 __device__ __forceinline__ f3 finish_ray(const SceneView &s, const f3 &o, const f3 &d, const f3 &inv, float t,
                                          bool hit, f3 sun, int &refine_samples) {
     refine_samples = 0;
     if (hit) {
-        float tb = t - 1.5f;
-        f3 h = {o.x + d.x * tb, o.y + d.y * tb, o.z + d.z * tb};
-        int stx = d.x > 0.0f ? 1 : -1, sty = d.y > 0.0f ? 1 : -1, stz = d.z > 0.0f ? 1 : -1;
-        float c1x = (floorf(h.x) - h.x) / d.x, c1y = (floorf(h.y) - h.y) / d.y, c1z = (floorf(h.z) - h.z) / d.z;
-        f3 tMax = {gmax(c1x, c1x + inv.x), gmax(c1y, c1y + inv.y), gmax(c1z, c1z + inv.z)};
-        f3 tDelta = {fabsf(inv.x), fabsf(inv.y), fabsf(inv.z)};   // 1/|d| == |1/d| exactly
-        int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
-        float ax = 0.0f, ay = 0.0f, az = 0.0f;
-        int id;
-        int vid = get_voxel(s, vx, vy, vz, id);
-        int ns = 1;
-        int it = 0;
-        while ((it++ <= 4) && (vid == 0)) {
-            ax = ((tMax.x <= tMax.y) && (tMax.x <= tMax.z)) ? 1.0f : 0.0f;
-            ay = ((tMax.x >= tMax.y) && (tMax.y <= tMax.z)) ? 1.0f : 0.0f;
-            az = ((tMax.z <= tMax.x) && (tMax.z <= tMax.y)) ? 1.0f : 0.0f;
-            vx += stx * (int)ax; vy += sty * (int)ay; vz += stz * (int)az;
-            tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
-            vid = get_voxel(s, vx, vy, vz, id);
-            ns++;
-        }
-        refine_samples = ns;
-        f3 n = {-((float)stx * ax), -((float)sty * ay), -((float)stz * az)};
-        float tf = (tMax.x - tDelta.x) * ax + (tMax.y - tDelta.y) * ay + (tMax.z - tDelta.z) * az;
+        f3 n;
+        float tf;
+        int vid;
+        refine_hit(s, o, d, inv, t, n, tf, vid, refine_samples);
         const float *m = s.materials + 6 * (vid & 255);
         float mr = __ldg(m), mg = __ldg(m + 1), mb = __ldg(m + 2), me = __ldg(m + 4);
         f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
@@ -271,6 +282,38 @@ __device__ __forceinline__ f3 finish_ray(const SceneView &s, const f3 &o, const 
     l.y += 1.0f * (0.81f * 0.1f);
     l.z += 1.0f * (0.92f * 0.1f);
     return l;
+}
+
+// ---- CastRay_fast's coarse loop for one ray, start to end (one-thread-per-ray kernels) ----------
+// fast = the scene passed validation (see march_step_fast).  Returns hit; t = fraction at loop exit.
+__device__ __forceinline__ bool march_ray(const SceneView &s, const MarchConsts &mc, bool fast, const f3 &o, const f3 &d,
+                                          const f3 &inv, float &t) {
+    t = 0.0f;
+    if (fast) {
+        const uint3 wsbits = {__float_as_uint(mc.wsx), __float_as_uint(mc.wsy), __float_as_uint(mc.wsz)};
+        const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
+        float t_pre;
+        bool hit;
+        while (!march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit)) {}
+        if (hit) return true;
+        // Ended without an in-world hit.  Unlike the probe rays, whose origins are built by setup_ray, these
+        // origins come from the caller: a position of -0.0 or NaN is "out" for the bit test but not for
+        // pos < 0 -- such a ray (never seen in practice) is simply redone by the general loop below.
+        const float px = o.x + d.x * t_pre, py = o.y + d.y * t_pre, pz = o.z + d.z * t_pre;
+        const bool fast_out = __float_as_uint(px) >= wsbits.x || __float_as_uint(py) >= wsbits.y || __float_as_uint(pz) >= wsbits.z;
+        const bool out = px < 0.0f || py < 0.0f || pz < 0.0f || px >= mc.wsx || py >= mc.wsy || pz >= mc.wsz;
+        if (fast_out == out) {
+            if (!out) return false;                                   // in-world, ended by distance
+            int id;
+            if (get_voxel(s, f2i(px), f2i(py), f2i(pz), id) == 0) return false;
+            t = t_pre;                                                // the deferred sample hit (resolve_pending)
+            return true;
+        }
+        t = 0.0f;
+    }
+    int st;
+    do { st = march_step(s, mc, o, d, inv, t); } while (st == 0);
+    return st == 1;
 }
 
 // Whole ray, one thread (the one-workgroup-per-CTA kernel).

@@ -175,6 +175,62 @@ def update(scene: Scene, field_old, requests, time_seed, size=1, shift=0, nthrea
     return res
 
 
+# ---- glossy.frag ---------------------------------------------------------------
+class GlossyView(C.Structure):
+    _fields_ = [("campos", C.c_float * 3), ("camdir", C.c_float * 3), ("horizline_scaled", C.c_float * 3),
+                ("vertiline_scaled", C.c_float * 3), ("global_light_dir", C.c_float * 3),
+                ("frame_size", C.c_float * 2)]
+
+
+def glossy_view(view):
+    v = GlossyView()
+    for k in ("campos", "camdir", "horizline_scaled", "vertiline_scaled", "global_light_dir"):
+        getattr(v, k)[:] = [float(np.float32(x)) for x in view[k]]
+    v.frame_size[:] = [float(np.float32(x)) for x in view["frame_size"]]
+    return v
+
+
+def camera_view(campos, camdir, width, height, pixels_in_voxel=5.0, light_dir=(0.5, 0.5, -0.9)):
+    """The uniform-block fields as Camera::updateCamera + start_raygen fill them (internal_types.hpp:54-66,
+    internal_render.cpp:921-934,1580-1592): double precision on the host, rounded to f32 for the UBO."""
+    d = np.asarray(camdir, np.float64); d = d / np.linalg.norm(d)
+    plane = np.array([d[0], d[1], 0.0]); plane = plane / np.linalg.norm(plane)
+    horiz = np.cross(plane, [0.0, 0.0, 1.0]); horiz = horiz / np.linalg.norm(horiz)
+    verti = np.cross(d, horiz); verti = verti / np.linalg.norm(verti)
+    view_size = np.array([width, height], np.float64) / pixels_in_voxel
+    ld = np.asarray(light_dir, np.float64); ld = ld / np.linalg.norm(ld)
+    return dict(campos=np.asarray(campos, np.float64).astype(np.float32), camdir=d.astype(np.float32),
+                horizline_scaled=(horiz * view_size[0] / 2.0).astype(np.float32),
+                vertiline_scaled=(verti * view_size[1] / 2.0).astype(np.float32),
+                global_light_dir=ld.astype(np.float32), frame_size=np.array([width, height], np.float32))
+
+
+def gbuffer(scene: Scene, view, width, height):
+    """Fabricated G-buffer (test input): mat_norm uint8 [h,w,4], depth float32 [h,w]."""
+    mn = np.zeros((height, width, 4), np.uint8)
+    dp = np.zeros((height, width), np.float32)
+    v = glossy_view(view)
+    lib().lum_oracle_gbuffer(C.byref(scene.c), C.byref(v), C.c_int(width), C.c_int(height), _p(mn), _p(dp))
+    return mn, dp
+
+
+def glossy(scene: Scene, field, view, mat_norm, depth, frame=None, nthreads=0):
+    """Returns dict(frame float32 [h,w,4], covered uint8 [h,w], samples uint32 [h,w], coarse uint32 [h,w])."""
+    field = np.ascontiguousarray(field, np.uint32).reshape(-1)
+    assert field.size == scene.cells
+    mn = np.ascontiguousarray(mat_norm, np.uint8)
+    h, w = mn.shape[:2]
+    dp = np.ascontiguousarray(depth, np.float32)
+    fr = np.zeros((h, w, 4), np.float32) if frame is None else np.array(frame, np.float32, copy=True)
+    cov = np.zeros((h, w), np.uint8)
+    ns = np.zeros((h, w), np.uint32)
+    nc = np.zeros((h, w), np.uint32)
+    v = glossy_view(view)
+    lib().lum_oracle_glossy(C.byref(scene.c), _p(field), C.byref(v), C.c_int(w), C.c_int(h), _p(mn), _p(dp),
+                            _p(fr), _p(cov), _p(ns), _p(nc), C.c_int(nthreads))
+    return dict(frame=fr, covered=cov, samples=ns, coarse=nc)
+
+
 def shift_field(field, dims, dx, dy, dz):
     wx, wy, wz = dims
     field = np.ascontiguousarray(field, np.uint32).reshape(-1)
@@ -307,3 +363,38 @@ def ref_glsl_map_model(world, bricks, model, placement):
                                      _p(m), C.c_int(sx), C.c_int(sy), C.c_int(sz), placement.inverse_trans,
                                      placement.map_shift, placement.map_area)
     assert rc == 0, rc
+
+
+_REF_GLOSSY_PATH = os.path.join(_HERE, "_ref", "libref_glossy_glsl.so")
+_ref_glossy = None
+
+
+def ref_glossy_available() -> bool:
+    return os.path.exists(_REF_GLOSSY_PATH)
+
+
+def ref_glsl_glossy(scene: Scene, field, view, mat_norm, depth, frame=None):
+    """The reference's own shaders/glossy.frag (oracle/ref_glossy_glsl.cpp), one invocation per covered
+    fragment; same arguments and result as glossy(), plus fetches = texelFetch(blocks) calls per fragment
+    (= 2 + 2*coarse iterations + refinement samples)."""
+    global _ref_glossy
+    if _ref_glossy is None:
+        _ref_glossy = C.CDLL(_REF_GLOSSY_PATH)
+        _ref_glossy.ref_glsl_glossy.restype = C.c_int
+    field = np.ascontiguousarray(field, np.uint32).reshape(-1)
+    assert field.size == scene.cells
+    mn = np.ascontiguousarray(mat_norm, np.uint8)
+    h, w = mn.shape[:2]
+    dp = np.ascontiguousarray(depth, np.float32)
+    fr = np.zeros((h, w, 4), np.float32) if frame is None else np.array(frame, np.float32, copy=True)
+    cov = np.zeros((h, w), np.uint8)
+    nf = np.zeros((h, w), np.uint32)
+    v = np.concatenate([np.asarray(view[k], np.float32).reshape(-1) for k in
+                        ("campos", "camdir", "horizline_scaled", "vertiline_scaled", "global_light_dir", "frame_size")])
+    v = np.ascontiguousarray(v, np.float32)
+    assert v.size == 17
+    rc = _ref_glossy.ref_glsl_glossy(C.c_int(scene.wx), C.c_int(scene.wy), C.c_int(scene.wz), _p(scene.world),
+                                     _p(scene.bricks), C.c_int(scene.bricks.shape[0]), _p(scene.materials), _p(field),
+                                     _p(v), C.c_int(w), C.c_int(h), _p(mn), _p(dp), _p(fr), _p(cov), _p(nf))
+    assert rc == 0, rc
+    return dict(frame=fr, covered=cov, fetches=nf)

@@ -58,6 +58,8 @@ template <class T> struct tvec2 {
     tvec2(T a, T b) : x(a), y(b) {}
     explicit tvec2(T s) : x(s), y(s) {}
     template <class U> explicit(!implicit_ok<U, T>) tvec2(const tvec2<U>& o) : x((T)o.x), y((T)o.y) {}
+    template <class U> explicit tvec2(const tvec4<U>& o);            // vec2(gl_FragCoord): first two components
+    friend tvec2 operator+(tvec2 a) { return a; }
     T& operator[](int i) { return i == 0 ? x : y; }
     T operator[](int i) const { return i == 0 ? x : y; }
     GLSL_VEC_OPS(tvec2, 2)
@@ -97,13 +99,18 @@ template <class T> struct tvec4 {
     T operator[](int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
     tvec3<T> xyz() const { return tvec3<T>(x, y, z); }
     tvec3<T> rgb() const { return tvec3<T>(x, y, z); }
+    tvec3<T> gba() const { return tvec3<T>(y, z, w); }
+    tvec2<T> xy() const { return tvec2<T>(x, y); }
     GLSL_VEC_OPS(tvec4, 4)
 };
+template <class T> template <class U> tvec2<T>::tvec2(const tvec4<U>& o) : x((T)o.x), y((T)o.y) {}
 
 typedef tvec2<float> vec2;   typedef tvec3<float> vec3;   typedef tvec4<float> vec4;
 typedef tvec2<int> ivec2;    typedef tvec3<int> ivec3;    typedef tvec4<int> ivec4;
 typedef tvec3<uint> uvec3;   typedef tvec4<uint> uvec4;
 typedef tvec3<bool> bvec3;
+// GLSL converts an unsigned vector implicitly when it meets a float (glossy.frag:369 `uvec3 / 255.0`)
+inline tvec3<float> operator/(const tvec3<uint>& a, float b) { return tvec3<float>((float)a.x, (float)a.y, (float)a.z) / b; }
 
 // Column-major 4x4 matrix.  mat4 * vec4 accumulates the columns in order 0,1,2,3, one rounding per
 // product and per sum (D11).
@@ -141,7 +148,12 @@ inline vec3 cross(vec3 a, vec3 b) { return vec3(a.y * b.z - b.y * a.z, a.z * b.x
 inline bvec3 lessThan(vec3 a, vec3 b) { return bvec3(a.x < b.x, a.y < b.y, a.z < b.z); }
 inline bvec3 greaterThan(vec3 a, vec3 b) { return bvec3(a.x > b.x, a.y > b.y, a.z > b.z); }
 inline bvec3 greaterThanEqual(vec3 a, vec3 b) { return bvec3(a.x >= b.x, a.y >= b.y, a.z >= b.z); }
+inline bvec3 lessThan(ivec3 a, ivec3 b) { return bvec3(a.x < b.x, a.y < b.y, a.z < b.z); }
+inline bvec3 greaterThanEqual(ivec3 a, ivec3 b) { return bvec3(a.x >= b.x, a.y >= b.y, a.z >= b.z); }
 inline bool any(bvec3 v) { return v.x || v.y || v.z; }
+inline float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
+// reflect(I, N) = I - 2.0 * dot(N, I) * N (GLSL 4.50 section 8.5), evaluated left to right (D14)
+inline vec3 reflect(vec3 I, vec3 N) { return I - 2.0f * dot(N, I) * N; }
 
 // ---- A2B10G10R10 unorm (internal_render.hpp:456; D7) ----
 inline vec3 unpack_rgb10(uint32_t w) {
@@ -170,6 +182,9 @@ struct sampler2D {           // material palette R32F 6 x 256 (internal_render.c
 struct sampler3D {           // radiance field A2B10G10R10, LINEAR + REPEAT, normalised coords (setup.cpp:75-81)
     const uint32_t* data = nullptr; ivec3 size;
 };
+struct usampler2D {          // G-buffer material + normal, R8G8B8A8_UINT (internal_render.hpp:455), x + W*y
+    const uint8_t* data = nullptr; ivec2 size;
+};
 struct image3D {
     uint32_t* data = nullptr; ivec3 size;
 };
@@ -188,6 +203,20 @@ inline uvec4 texelFetch(const usampler3D& t, ivec3 p, int) {
 inline vec4 texelFetch(const sampler2D& t, ivec2 p, int) {
     if (p.x < 0 || p.y < 0 || p.x >= t.size.x || p.y >= t.size.y) return vec4(0, 0, 0, 0);
     return vec4(t.data[p.x + t.size.x * p.y], 0, 0, 1);
+}
+inline uvec4 texelFetch(const usampler2D& t, ivec2 p, int) {
+    if (p.x < 0 || p.y < 0 || p.x >= t.size.x || p.y >= t.size.y) return uvec4(0, 0, 0, 0);
+    const uint8_t* q = t.data + 4 * (p.x + (int64_t)t.size.x * p.y);
+    return uvec4(q[0], q[1], q[2], q[3]);
+}
+inline ivec2 textureSize(const usampler2D& t, int) { return t.size; }
+// texture() on the NEAREST sampler the glossy pass binds for the depth attachment (internal_render.cpp:278,
+// nearestSampler): texel floor(uv * size), clamped to the edge
+inline vec4 texture(const sampler2D& t, vec2 uv) {
+    int x = (int)::floorf(uv.x * (float)t.size.x), y = (int)::floorf(uv.y * (float)t.size.y);
+    x = x < 0 ? 0 : (x >= t.size.x ? t.size.x - 1 : x);
+    y = y < 0 ? 0 : (y >= t.size.y ? t.size.y - 1 : y);
+    return vec4(t.data[x + t.size.x * y], 0, 0, 1);
 }
 inline vec4 texelFetch(const sampler3D& t, ivec3 p, int) {
     if (!inside(p, t.size)) return vec4(0, 0, 0, 0);
@@ -248,6 +277,7 @@ inline void imageStore(uimage3D& t, ivec3 p, uvec4 c) {
 struct SubgroupYield {};
 struct ShaderBase {
     uvec3 gl_GlobalInvocationID;
+    vec4 gl_FragCoord;                // fragment shaders (glossy.frag)
     uint gl_SubgroupSize = 32;
     uint gl_SubgroupID = 0;
     uint gl_SubgroupInvocationID = 0;

@@ -369,6 +369,130 @@ int lum_oracle_update_ex(const LumOracleScene *s, const uint32_t *field_old, uin
     return used;
 }
 
+/* ---- shaders/glossy.frag as a CPU pass ------------------------------- */
+/* CastRay_fast of glossy.frag:119-226 is statement for statement the one of radiance.comp:183-291
+ * (checked by running both shader texts, tests/test_ref_glsl.py), so cast_ray_fast() above serves both.
+ * One invocation per fragment of a width x height target; citations are glossy.frag lines. */
+void lum_oracle_glossy(const LumOracleScene *s, const uint32_t *field, const LumOracleGlossyView *v,
+                       int width, int height, const uint8_t *mat_norm, const float *depth,
+                       float *frame, uint8_t *covered, uint32_t *samples, uint32_t *coarse, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+    for (int py = 0; py < height; py++)
+    for (int px = 0; px < width; px++) {
+        size_t pi = (size_t)py * (size_t)width + (size_t)px;
+        const uint8_t *mn = mat_norm + 4 * pi;
+        const float *m = s->materials + 6 * (size_t)mn[0];               /* GetMat(load_mat(pix)) :443,:85-96 */
+        float rough = m[5];
+        int cov = !(rough > 0.5f);                                       /* fillStencilGlossy.frag:34-36 */
+        if (covered) covered[pi] = (uint8_t)cov;
+        if (samples) samples[pi] = 0;
+        if (coarse) coarse[pi] = 0;
+        if (!cov) continue;
+        v3 dir = { v->camdir[0], v->camdir[1], v->camdir[2] };           /* :444 */
+        float fcx = (float)px + 0.5f, fcy = (float)py + 0.5f;            /* gl_FragCoord.xy */
+        float cx = fcx / v->frame_size[0] * 2.0f - 1.0f;                 /* :446 */
+        float cy = fcy / v->frame_size[1] * 2.0f - 1.0f;
+        float dep = depth[pi] * 1000.0f;                                 /* load_depth :377-382 */
+        v3 origin = {                                                    /* get_origin_from_depth :41-47 */
+            ((v->campos[0] + v->horizline_scaled[0] * cx) + v->vertiline_scaled[0] * cy) + v->camdir[0] * dep,
+            ((v->campos[1] + v->horizline_scaled[1] * cx) + v->vertiline_scaled[1] * cy) + v->camdir[1] * dep,
+            ((v->campos[2] + v->horizline_scaled[2] * cx) + v->vertiline_scaled[2] * cy) + v->camdir[2] * dep };
+        v3 normal = { (float)mn[1] / 255.0f * 2.0f - 1.0f,               /* load_norm :367-371 */
+                      (float)mn[2] / 255.0f * 2.0f - 1.0f,
+                      (float)mn[3] / 255.0f * 2.0f - 1.0f };
+        v3 light = { 0.0f, 0.0f, 0.0f }, refl = { 1.0f, 1.0f, 1.0f };    /* :450-451 */
+        /* ProcessHit(origin, direction, 0, normal, mat, ...) :454-456, :312-326 */
+        origin.x = origin.x + 0.0f * dir.x; origin.y = origin.y + 0.0f * dir.y; origin.z = origin.z + 0.0f * dir.z; /* :316 */
+        v3 bp = { (origin.x + normal.x * 16.0f) / 16.0f, (origin.y + normal.y * 16.0f) / 16.0f,
+                  (origin.z + normal.z * 16.0f) / 16.0f };               /* sample_radiance :98-103 */
+        v3 g = gather(s, field, bp);
+        refl.x *= m[0]; refl.y *= m[1]; refl.z *= m[2];                  /* :322 */
+        light.x += refl.x * (m[4] + g.x);                                /* :323 */
+        light.y += refl.y * (m[4] + g.y);
+        light.z += refl.z * (m[4] + g.z);
+        {   /* reflect(I,N) = I - 2.0*dot(N,I)*N, GLSL 4.50 s8.5, left to right (decree 14) :325 */
+            float k = 2.0f * g_dot(normal, dir);
+            dir.x = dir.x - k * normal.x; dir.y = dir.y - k * normal.y; dir.z = dir.z - k * normal.z;
+        }
+        /* trace_glossy_ray :328-360 */
+        float fraction = 0.0f;
+        v3 n2 = { 0.0f, 0.0f, 0.0f };
+        mat_t mat = { { 0.0f, 0.0f, 0.0f }, 0.0f };
+        int voxel = 0, ncoarse = 0, nrefine = 0;
+        int hit = cast_ray_fast(s, origin, dir, &fraction, &n2, &mat, &voxel, &ncoarse, &nrefine); /* :341 */
+        if (samples) samples[pi] = (uint32_t)(ncoarse + nrefine);
+        if (coarse) coarse[pi] = (uint32_t)ncoarse;
+        if (hit) {                                                       /* :342-345 */
+            v3 x = { origin.x + fraction * dir.x, origin.y + fraction * dir.y, origin.z + fraction * dir.z };
+            v3 bp2 = { (x.x + n2.x * 16.0f) / 16.0f, (x.y + n2.y * 16.0f) / 16.0f, (x.z + n2.z * 16.0f) / 16.0f };
+            v3 g2 = gather(s, field, bp2);
+            refl.x *= mat.color[0]; refl.y *= mat.color[1]; refl.z *= mat.color[2];
+            light.x += refl.x * (mat.emmit + g2.x);
+            light.y += refl.y * (mat.emmit + g2.y);
+            light.z += refl.z * (mat.emmit + g2.z);
+        } else {                                                         /* :346-357 */
+            v3 gld = { v->global_light_dir[0], v->global_light_dir[1], v->global_light_dir[2] };
+            float glp = -g_dot(dir, gld);                                /* :349 */
+            if (glp > 0.9f) {                                            /* :350-353 */
+                float w = glp - 0.9f;
+                light.x += (0.9f * 0.5f) * refl.x * w * 10.0f;
+                light.y += (0.9f * 0.5f) * refl.y * w * 10.0f;
+                light.z += (0.6f * 0.5f) * refl.z * w * 10.0f;
+            }
+            light.x += (0.53f * 0.1f) * refl.x;                          /* :356 */
+            light.y += (0.81f * 0.1f) * refl.y;
+            light.z += (0.92f * 0.1f) * refl.z;
+        }
+        frame[4 * pi + 0] = light.x / 8.0f;                              /* :490, encode_color :435-437 */
+        frame[4 * pi + 1] = light.y / 8.0f;
+        frame[4 * pi + 2] = light.z / 8.0f;
+        frame[4 * pi + 3] = 1.0f - rough;
+    }
+}
+
+/* A plausible G-buffer for the glossy tests and bench: what the raster passes would leave for an
+ * orthographic camera looking along camdir (start_raygen, internal_render.cpp:1580-1592).  NOT a restatement
+ * of anything: it only fabricates inputs (first solid voxel along the view ray by fine sampling). */
+void lum_oracle_gbuffer(const LumOracleScene *s, const LumOracleGlossyView *v, int width, int height,
+                        uint8_t *mat_norm, float *depth) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (int py = 0; py < height; py++)
+    for (int px = 0; px < width; px++) {
+        size_t pi = (size_t)py * (size_t)width + (size_t)px;
+        float cx = ((float)px + 0.5f) / v->frame_size[0] * 2.0f - 1.0f;
+        float cy = ((float)py + 0.5f) / v->frame_size[1] * 2.0f - 1.0f;
+        double o[3], d[3] = { v->camdir[0], v->camdir[1], v->camdir[2] };
+        for (int k = 0; k < 3; k++) o[k] = (double)v->campos[k] + (double)v->horizline_scaled[k] * cx + (double)v->vertiline_scaled[k] * cy;
+        int found = 0, vox = 0;
+        i3 prev = { 0x7fffffff, 0, 0 }, cur = { 0, 0, 0 };
+        double t = 0.0;
+        for (; t < 1000.0; t += 0.125) {
+            v3 p = { (float)(o[0] + d[0] * t), (float)(o[1] + d[1] * t), (float)(o[2] + d[2] * t) };
+            if (p.x < 0.0f || p.y < 0.0f || p.z < 0.0f || p.x >= 16.0f * s->wx || p.y >= 16.0f * s->wy || p.z >= 16.0f * s->wz) continue;
+            cur = trunc3(p);
+            int bid;
+            get_voxel(s, cur, &vox, &bid);
+            if (vox != 0) { found = 1; break; }
+            prev = cur;
+        }
+        uint8_t *mn = mat_norm + 4 * pi;
+        if (!found) { mn[0] = 0; mn[1] = mn[2] = mn[3] = 128; depth[pi] = 1.0f; continue; }
+        int n[3] = { 0, 0, 0 };
+        if (prev.x != 0x7fffffff) {
+            if (prev.x != cur.x) n[0] = prev.x - cur.x; else if (prev.y != cur.y) n[1] = prev.y - cur.y; else if (prev.z != cur.z) n[2] = prev.z - cur.z;
+        }
+        if (!n[0] && !n[1] && !n[2]) n[2] = 1;
+        for (int k = 0; k < 3; k++) { int c = n[k] > 0 ? 255 : (n[k] < 0 ? 0 : 128); mn[1 + k] = (uint8_t)c; }
+        mn[0] = (uint8_t)vox;
+        depth[pi] = (float)(t / 1000.0);
+    }
+}
+
 /* ---- update_radiance request list (internal_render.cpp:1142-1169) ------------------ */
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 int64_t lum_oracle_build_requests(int wx, int wy, int wz, const int16_t *world,

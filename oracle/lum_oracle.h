@@ -74,6 +74,22 @@ void lum_oracle_get_voxel(const LumOracleScene *s, int x, int y, int z, int out[
 /* sample_radiance gather (radiance.comp:161-166 + sampler setup.cpp:75-81) at block-space bp. */
 void lum_oracle_gather(const LumOracleScene *s, const uint32_t *field, const float bp[3], float rgb[3]);
 
+/* shaders/glossy.frag as a CPU pass.  View = the uniform-block fields the shader reads
+ * (shaders/common/ubo.glsl).  mat_norm uint8 [h][w][4] (R8G8B8A8_UINT: material, normal), depth float [h][w]
+ * in [0,1]; frame float [h][w][4] = fragment colour before the blend (written where covered);
+ * covered / samples (per-pixel GetVoxel calls of the mirror ray) / coarse (iterations of its coarse loop)
+ * may be NULL. */
+typedef struct {
+    float campos[3], camdir[3], horizline_scaled[3], vertiline_scaled[3], global_light_dir[3];
+    float frame_size[2];
+} LumOracleGlossyView;
+void lum_oracle_glossy(const LumOracleScene *s, const uint32_t *field, const LumOracleGlossyView *v,
+                       int width, int height, const uint8_t *mat_norm, const float *depth,
+                       float *frame, uint8_t *covered, uint32_t *samples, uint32_t *coarse, int nthreads);
+/* Test-input fabrication (not a restatement): G-buffer of an orthographic view of the scene. */
+void lum_oracle_gbuffer(const LumOracleScene *s, const LumOracleGlossyView *v, int width, int height,
+                        uint8_t *mat_norm, float *depth);
+
 /* update_radiance request list (internal_render.cpp:1142-1169).
  * out: int16 x,y,z,w per request; returns the count (may exceed cap: nothing is written past cap). */
 int64_t lum_oracle_build_requests(int wx, int wy, int wz, const int16_t *world,
