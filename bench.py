@@ -343,6 +343,74 @@ def measure_api_config3(frames=64, warmup=8):
             "value": n * RAYS * frames / dt, "unit": UNIT, "timing": "host wall clock, includes the host side of the API"}
 
 
+def measure_glossy(torch, device, steps=20, warmup=5):
+    """Secondary line: the glossy pass (shaders/glossy.frag as lumcu_glossy) over a 1920x1080
+    G-buffer of the demo world -- a mirror floor at z = 24 voxels seen by the demo's orthographic start
+    camera (internal_types.hpp:54-66), every fragment covered, one mirror ray each.  value = device-resident
+    (lumcu_glossy_device on GPU tensors, CUDA events); e2e = lumcu_glossy with host buffers."""
+    import ctypes as C
+    import lum_b200
+    from lum_b200 import scenes
+    d = scenes.demo_scene()
+    w, h = 1920, 1080
+    st = lum_b200.RadianceStage((48, 48, 16), d["bricks"].shape[0], device=device)
+    st.upload_world(d["world"]); st.upload_bricks(0, d["bricks"]); st.upload_materials(d["materials"])
+    st.build_requests()
+    for i in range(8):                                   # a lit field to sample
+        st.update(i)
+    cd = np.array([0.61, 1.0, -0.8]); cd /= np.linalg.norm(cd)
+    plane = np.array([cd[0], cd[1], 0.0]); plane /= np.linalg.norm(plane)
+    hz = np.cross(plane, [0, 0, 1.0]); hz /= np.linalg.norm(hz)
+    vt = np.cross(cd, hz); vt /= np.linalg.norm(vt)
+    vs = np.array([w, h]) / 5.0                          # pixelsInVoxel = 5
+    campos = np.array([60.0, 0.0, 194.0])
+    view = dict(campos=campos, camdir=cd, horizline_scaled=hz * vs[0] / 2, vertiline_scaled=vt * vs[1] / 2,
+                global_light_dir=np.array([0.5, 0.5, -0.9]) / np.linalg.norm([0.5, 0.5, -0.9]), frame_size=[w, h])
+    cx = ((np.arange(w) + 0.5) / w * 2 - 1)[None, :]
+    cy = ((np.arange(h) + 0.5) / h * 2 - 1)[:, None]
+    z = campos[2] + view["horizline_scaled"][2] * cx + view["vertiline_scaled"][2] * cy
+    depth = ((z - 24.0) / -cd[2] / 1000.0).astype(np.float32)
+    glossy_ids = np.nonzero(d["materials"][:, 5] <= 0.5)[0]
+    mat = int(glossy_ids[glossy_ids > 0][0])
+    mn = np.zeros((h, w, 4), np.uint8); mn[..., 0] = mat; mn[..., 1:3] = 128; mn[..., 3] = 255
+    dev = torch.device(f"cuda:{device}")
+    t_mn, t_dp = torch.from_numpy(mn).to(dev), torch.from_numpy(depth).to(dev)
+    t_fr = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+    stream = torch.cuda.ExternalStream(st.stream(), device=device)
+    v = st.glossy_view(view)
+    torch.cuda.synchronize()
+
+    def resident():
+        rc = st.lib.lumcu_glossy_device(st.ctx, C.byref(v), w, h, t_mn.data_ptr(), t_dp.data_ptr(), t_fr.data_ptr(), 0)
+        assert rc == 0, st.lib.lumcu_last_error()
+
+    fr_host = np.zeros((h, w, 4), np.float32)
+
+    def e2e():
+        rc = st.lib.lumcu_glossy(st.ctx, C.byref(v), w, h, mn.ctypes.data_as(C.c_void_p), depth.ctypes.data_as(C.c_void_p),
+                                 fr_host.ctypes.data_as(C.c_void_p), None)
+        assert rc == 0, st.lib.lumcu_last_error()
+
+    out = {}
+    for name, fn in (("resident", resident), ("e2e", e2e)):
+        for _ in range(warmup):
+            fn()
+        with torch.cuda.stream(stream):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            torch.cuda.synchronize()
+            for k in range(steps):
+                ev[k][0].record(stream); fn(); ev[k][1].record(stream)
+            torch.cuda.synchronize()
+        out[name] = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    covered = int(np.count_nonzero(np.any(fr_host != 0, axis=2)))
+    st.close()
+    return {"workload": "demo world, 1920x1080 G-buffer (mirror floor at z=24, orthographic demo camera), glossy.frag as lumcu_glossy",
+            "fragments": w * h, "covered": covered, "ms_per_frame": out["resident"], "value": w * h / (out["resident"] * 1e-3),
+            "unit": "mirror rays/s", "e2e": {"ms_per_frame": out["e2e"], "value": w * h / (out["e2e"] * 1e-3),
+                                             "h2d_bytes_per_step": int(mn.nbytes + depth.nbytes + fr_host.nbytes),
+                                             "d2h_bytes_per_step": int(fr_host.nbytes)}}
+
+
 def cpu_baseline(scene, budget_s, threads=0):
     """The oracle port on the host cores, on a bounded strided sample of the request list."""
     import oracle as O
@@ -390,6 +458,20 @@ def run_reference(args, rank):
                              "sample": base["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    # Informational: the reference's OWN radiance.comp text executed on the CPU (oracle/_ref, built where the
+    # reference tree exists).  It is NOT the timed arm: the GLSL shim runs every invocation twice (subgroupAdd
+    # is resolved in two passes) and its requests are i8vec4, so only probes with coordinates <= 127 qualify.
+    try:
+        if O.ref_glsl_available():
+            sub = sample[(sample[:, :3].max(axis=1) <= 127)][:256]
+            if len(sub):
+                t0 = time.perf_counter()
+                O.ref_glsl_update(sc, f0, sub, 1)
+                dt2 = time.perf_counter() - t0
+                line["reference_shader_on_cpu"] = {"value": len(sub) * RAYS / dt2, "unit": UNIT, "probes": int(len(sub)),
+                                                   "what": "shaders/radiance.comp itself on oracle/glsl_shim.hpp, OpenMP over workgroups"}
+    except Exception as e:
+        line["reference_shader_on_cpu"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -419,6 +501,10 @@ def run_ours(args, rank, local_rank, world_size):
             extra["config3_api"] = json.loads(p.stdout.strip().splitlines()[-1])
         except Exception as e:
             extra["config3_api"] = {"error": repr(e)}
+        try:
+            extra["glossy"] = measure_glossy(torch, local_rank)
+        except Exception as e:
+            extra["glossy"] = {"error": repr(e)}
         extra["demo"] = {"workload": "demo (BASELINE configs[1]: 48x48x16 demo world, full recompute)",
                          "probes": dm["probes"], "rays": dm["rays"], "value": dm["value"], "unit": UNIT,
                          "ms_per_step": dm["ms_per_step"], "kernel_ms": dm["kernel_ms"],

@@ -479,6 +479,16 @@ void lum_oracle_gbuffer(const LumOracleScene *s, const LumOracleGlossyView *v, i
             get_voxel(s, cur, &vox, &bid);
             if (vox != 0) { found = 1; break; }
             prev = cur;
+            if (bid == 0) {     /* empty block: hop over the lattice points that lie strictly inside it */
+                double te = 1e30;
+                for (int k = 0; k < 3; k++) {
+                    double pk = o[k] + d[k] * t, c0 = 16.0 * floor(pk / 16.0);
+                    if (d[k] > 0.0) te = fmin(te, (c0 + 16.0 - pk) / d[k]);
+                    else if (d[k] < 0.0) te = fmin(te, (c0 - pk) / d[k]);
+                }
+                double hop = floor((te - 0.5) / 0.125) * 0.125;       /* stay 0.5 short of the face */
+                if (hop > 0.0) t += hop;
+            }
         }
         uint8_t *mn = mat_norm + 4 * pi;
         if (!found) { mn[0] = 0; mn[1] = mn[2] = mn[3] = 128; depth[pi] = 1.0f; continue; }
