@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(128) glossy_kernel(SceneView s, GlossyArgs a) 
         f3 n2;
         float tf;
         int vid, nr;
-        refine_hit(s, o, d, inv, t, n2, tf, vid, nr);
+        refine_hit<false>(s, o, d, inv, t, n2, tf, vid, nr);
         const float *m2 = s.materials + 6 * (vid & 255);
         const float r2 = __ldg(m2), g2 = __ldg(m2 + 1), b2 = __ldg(m2 + 2), e2 = __ldg(m2 + 4);
         const f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
