@@ -61,15 +61,14 @@ __device__ __forceinline__ int get_voxel(const SceneView &s, int ix, int iy, int
     return v;
 }
 
-// c/1023 correctly rounded without the division subroutine: q0 = c*RN(1/1023), one Markstein
-// correction step with explicit FMAs.  Bit-identical to IEEE c/1023.0f for every c in [0,1023]
-// (verified exhaustively; tests/test_parity_gpu.py::test_unpack_all_codes).
+// c/1023 correctly rounded without the division subroutine: with r = RN(1/1023) and rl = RN(1/1023 - r),
+// c/1023 = c*r + c*rl up to a relative 2^-48, and fma(c, r, RN(c*rl)) rounds that sum once.  Bit-identical to
+// IEEE c/1023.0f for every c in [0,1023] (verified exhaustively; tests/test_parity_gpu.py::test_unpack_all_codes).
 __device__ __forceinline__ float unorm10_to_float(uint32_t c) {
     const float r = 1.0f / 1023.0f;
-    float fc = (float)c;
-    float q0 = fc * r;
-    float rem = __fmaf_rn(-1023.0f, q0, fc);
-    return __fmaf_rn(rem, r, q0);
+    const float rl = __uint_as_float(0x2b802008u);      // RN(1/1023 - r) = 0x1.00401p-40
+    const float fc = (float)c;
+    return __fmaf_rn(fc, r, fc * rl);
 }
 __device__ __forceinline__ f3 unpack10(uint32_t w) {
     return {unorm10_to_float(w & 1023u), unorm10_to_float((w >> 10) & 1023u), unorm10_to_float((w >> 20) & 1023u)};

@@ -238,6 +238,7 @@ struct PoolCta {
     PoolShared<NR, DEBUG> sm;
     unsigned short list[3][LIST];   // [0] = stragglers of pass 0, [1],[2] ping-pong afterwards
     short4 req[PPC];
+    float sub[PPC * (R < 32 ? 1 : R / 32)][3];   // subgroup means (phase D)
     int next, park[3], chunk;
 };
 
@@ -332,42 +333,44 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     __syncthreads();
 
     // ---- phase D: reduce + blend ----
-    for (int pr = warp; pr < nprobes; pr += NW) {
+    // The PPC*NSUB subgroup sums are spread over the warps (xor butterfly, the oracle's pinned tree); then one
+    // thread per probe forms the mean of its subgroups and blends, all probes of the batch side by side.
+    for (int sg = warp; sg < nprobes * NSUB; sg += NW) {
+        const int r = sg * SUB + lane;
+        const float4 lv = lane < SUB ? sm.a[r] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float lx = lv.x, ly = lv.y, lz = lv.z;
+#pragma unroll
+        for (int k = SUB / 2; k >= 1; k >>= 1) {
+            lx += __shfl_xor_sync(FULL, lx, k);
+            ly += __shfl_xor_sync(FULL, ly, k);
+            lz += __shfl_xor_sync(FULL, lz, k);
+        }
+        if (lane == 0) { cta.sub[sg][0] = lx / (float)SUB; cta.sub[sg][1] = ly / (float)SUB; cta.sub[sg][2] = lz / (float)SUB; }
+    }
+    __syncthreads();
+    if (tid < nprobes) {
+        const int pr = tid;
         float fr = 0.0f, fg = 0.0f, fb = 0.0f;
 #pragma unroll
-        for (int g = 0; g < NSUB; g++) {
-            const int r = pr * R + g * SUB + lane;
-            const float4 lv = lane < SUB ? sm.a[r] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            float lx = lv.x, ly = lv.y, lz = lv.z;
-#pragma unroll
-            for (int k = SUB / 2; k >= 1; k >>= 1) {
-                lx += __shfl_xor_sync(FULL, lx, k);
-                ly += __shfl_xor_sync(FULL, ly, k);
-                lz += __shfl_xor_sync(FULL, lz, k);
-            }
-            fr += lx / (float)SUB; fg += ly / (float)SUB; fb += lz / (float)SUB;
-        }
+        for (int g = 0; g < NSUB; g++) { fr += cta.sub[pr * NSUB + g][0]; fg += cta.sub[pr * NSUB + g][1]; fb += cta.sub[pr * NSUB + g][2]; }
         fr /= (float)NSUB; fg /= (float)NSUB; fb /= (float)NSUB;
-        if (lane == 0) {
-            const long long w = wg0 + pr;
-            const short4 rq = sm_req[pr];
-            if constexpr (DEBUG) {
-                if (a.dbg_pre_blend) {
-                    a.dbg_pre_blend[3 * w] = fr; a.dbg_pre_blend[3 * w + 1] = fg; a.dbg_pre_blend[3 * w + 2] = fb;
-                }
+        const long long w = wg0 + pr;
+        const short4 rq = sm_req[pr];
+        if constexpr (DEBUG) {
+            if (a.dbg_pre_blend) {
+                a.dbg_pre_blend[3 * w] = fr; a.dbg_pre_blend[3 * w + 1] = fg; a.dbg_pre_blend[3 * w + 2] = fb;
             }
-            uint32_t word = 0;
-            if ((unsigned)rq.x < (unsigned)s.wx && (unsigned)rq.y < (unsigned)s.wy && (unsigned)rq.z < (unsigned)s.wz) {
-                f3 old = unpack10(__ldg(s.field + (rq.x + s.wx * (rq.y + s.wy * rq.z))));
-                old.x = gmin(gmax(old.x, 0.0f), 1.0f); old.y = gmin(gmax(old.y, 0.0f), 1.0f); old.z = gmin(gmax(old.z, 0.0f), 1.0f);
-                const float t = a.reactiveness, omt = 1.0f - t;
-                word = pack10(old.x * omt + fr * t, old.y * omt + fg * t, old.z * omt + fb * t);
-            }
-            a.staged[w] = word;
         }
+        uint32_t word = 0;
+        if ((unsigned)rq.x < (unsigned)s.wx && (unsigned)rq.y < (unsigned)s.wy && (unsigned)rq.z < (unsigned)s.wz) {
+            f3 old = unpack10(__ldg(s.field + (rq.x + s.wx * (rq.y + s.wy * rq.z))));
+            old.x = gmin(gmax(old.x, 0.0f), 1.0f); old.y = gmin(gmax(old.y, 0.0f), 1.0f); old.z = gmin(gmax(old.z, 0.0f), 1.0f);
+            const float t = a.reactiveness, omt = 1.0f - t;
+            word = pack10(old.x * omt + fr * t, old.y * omt + fg * t, old.z * omt + fb * t);
+        }
+        a.staged[w] = word;
     }
 }
-
 
 #ifdef LUMCU_MINB             // tuning knob: min resident CTAs per SM asked of ptxas (a register cap)
 #define LUMCU_POOL_BOUNDS __launch_bounds__(THREADS, LUMCU_MINB)
