@@ -240,7 +240,26 @@ __device__ __forceinline__ float div_frac(float a, float d) {
     }
 }
 
-template <bool PROBE_DIRS>
+// GetVoxel for the validated device mirror (brick 0 empty, ids inside the palette): a voxel inside the world
+// needs neither the sign-correct division nor the block bounds test nor the capacity test; anything else takes
+// the general path.  Same result as get_voxel for every input.
+template <bool VALID>
+__device__ __forceinline__ int get_voxel_v(const SceneView &s, int ix, int iy, int iz) {
+    if constexpr (VALID) {
+        if ((unsigned)ix < (unsigned)(s.wx << 4) && (unsigned)iy < (unsigned)(s.wy << 4) && (unsigned)iz < (unsigned)(s.wz << 4)) {
+            const int bx = ix >> 4, by = iy >> 4, bz = iz >> 4;
+            const int id = __ldg(s.world + (bx + s.wx * (by + s.wy * bz)));
+            const int V = (ix * 16 + iy) * 16 + iz, B = (bx * 16 + by) * 16 + bz;
+            int v = 0;
+            if (id != 0) v = __ldg(s.bricks + (uint32_t)(id * 4096 + (V - 16 * B)));
+            return v;
+        }
+    }
+    int id;
+    return get_voxel(s, ix, iy, iz, id);
+}
+
+template <bool PROBE_DIRS, bool VALID>
 __device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, const f3 &d, const f3 &inv, float t,
                                            f3 &n, float &tf, int &vid, int &refine_samples) {
     float tb = t - 1.5f;
@@ -252,8 +271,7 @@ __device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, cons
     f3 tDelta = {fabsf(inv.x), fabsf(inv.y), fabsf(inv.z)};   // 1/|d| == |1/d| exactly
     int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
-    int id;
-    vid = get_voxel(s, vx, vy, vz, id);
+    vid = get_voxel_v<VALID>(s, vx, vy, vz);
     int ns = 1;
     int it = 0;
     while ((it++ <= 4) && (vid == 0)) {
@@ -262,7 +280,7 @@ __device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, cons
         az = ((tMax.z <= tMax.x) && (tMax.z <= tMax.y)) ? 1.0f : 0.0f;
         vx += stx * (int)ax; vy += sty * (int)ay; vz += stz * (int)az;
         tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
-        vid = get_voxel(s, vx, vy, vz, id);
+        vid = get_voxel_v<VALID>(s, vx, vy, vz);
         ns++;
     }
     refine_samples = ns;
@@ -272,6 +290,7 @@ __device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, cons
 
 // ---- after the march: refinement + hit shading, or sky (radiance.comp:246-288,316-347) ----
 // t = fraction at loop exit; hit = CastRay_fast's return value.  refine_samples counts GetVoxel calls.
+template <bool VALID>
 __device__ __forceinline__ f3 finish_ray(const SceneView &s, const f3 &o, const f3 &d, const f3 &inv, float t,
                                          bool hit, f3 sun, int &refine_samples) {
     refine_samples = 0;
@@ -279,7 +298,7 @@ __device__ __forceinline__ f3 finish_ray(const SceneView &s, const f3 &o, const 
         f3 n;
         float tf;
         int vid;
-        refine_hit<true>(s, o, d, inv, t, n, tf, vid, refine_samples);
+        refine_hit<true, VALID>(s, o, d, inv, t, n, tf, vid, refine_samples);
         const float *m = s.materials + 6 * (vid & 255);
         float mr = __ldg(m), mg = __ldg(m + 1), mb = __ldg(m + 2), me = __ldg(m + 4);
         f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
@@ -346,7 +365,7 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
     __syncwarp();   // reconverge before the long tail (early leavers would run it in separate passes)
     RayResult res;
     int nr;
-    res.light = finish_ray(s, o, d, inv, t, st == 1, sun, nr);
+    res.light = finish_ray<false>(s, o, d, inv, t, st == 1, sun, nr);
     res.hit = st == 1;
     res.samples = samples + nr;
     return res;

@@ -214,7 +214,7 @@ __device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const Scen
     bool hit = q.t > 0.0f;
     if constexpr (FAST) { if (!hit) hit = resolve_pending(s, mc, q.o, q.d, -q.t); }
     int nr;
-    const f3 l = finish_ray(s, q.o, q.d, q.inv, fabsf(q.t), hit, sun, nr);
+    const f3 l = finish_ray<FAST>(s, q.o, q.d, q.inv, fabsf(q.t), hit, sun, nr);
     sm.a[r].x = l.x; sm.a[r].y = l.y; sm.a[r].z = l.z;
     if constexpr (DEBUG) {
         const unsigned nsamp = (unsigned)q.ns + (unsigned)nr;
@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(128) glossy_kernel(SceneView s, GlossyArgs a) 
         f3 n2;
         float tf;
         int vid, nr;
-        refine_hit<false>(s, o, d, inv, t, n2, tf, vid, nr);
+        if (fast) refine_hit<false, true>(s, o, d, inv, t, n2, tf, vid, nr);
+        else refine_hit<false, false>(s, o, d, inv, t, n2, tf, vid, nr);
         const float *m2 = s.materials + 6 * (vid & 255);
         const float r2 = __ldg(m2), g2 = __ldg(m2 + 1), b2 = __ldg(m2 + 2), e2 = __ldg(m2 + 4);
         const f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
