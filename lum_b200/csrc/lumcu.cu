@@ -208,7 +208,7 @@ int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, lo
         case 64: return launch_pool_one<64, 64, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
 #else
         case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg)
-                                               : launch_pool_one<64, 256, 4, DEBUG>(c, sv, a, nwg);
+                                               : launch_pool_one<64, 256, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
 #endif
         case 128: return launch_pool_one<128, 256, 4, DEBUG>(c, sv, a, nwg);
         case 256: return launch_pool_one<256, 256, 4, DEBUG>(c, sv, a, nwg);
