@@ -190,7 +190,7 @@ class Runner:
 
     def step_resident(self, seed):
         if self.fused:
-            self.st.update_slab_exchange(seed, 1, 0, self.z0, self.z1)     # commit = exchange (peer stores)
+            self.st.update_shard_exchange(seed, 1, 0)          # interleaved shards; commit = exchange (peer stores)
         elif self.n > 1:
             self.st.update_slab(seed, 1, 0, self.z0, self.z1)
             self.exchange()                                                # NCCL all-gather
@@ -247,15 +247,14 @@ class Runner:
         out = []
         for i in range(warmup + steps):
             self.st.set_debug(lum_b200.DEBUG_PRE_BLEND if i >= warmup else 0)
-            if self.n > 1:
+            if self.fused:
+                self.st.update_shard_exchange(first_seed + i, 1, 0)       # the instrumented trace of this rank's shard
+                nwg = 1
+            elif self.n > 1:
                 b, e = self.st.slab_range(1, 0, self.z0, self.z1)
                 self.st.update_range(first_seed + i, 1, 0, b, e)
                 nwg = e - b
-                if self.fused:      # collective: make sure no peer is still reading before anyone writes
-                    self.st.wait_idle(); self.dist.barrier()
                 self.exchange()
-                if self.fused:
-                    self.st.wait_idle(); self.dist.barrier()
             else:
                 self.st.update(first_seed + i, 1, 0)
                 nwg = self.nreq
@@ -521,8 +520,8 @@ def run_ours(args, rank, local_rank, world_size):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": RAYS,
-                           "rays_per_step": m["rays"], "parallelism": (f"probe z-slabs x{world_size} + " + ("commit fused with the exchange (NVLink peer stores, flag barriers)"
-                                                                              if runner.fused else "NCCL field all-gather"))
+                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + ("interleaved chunks of 3072, commit fused with the exchange (NVLink peer stores, flag barriers)"
+                                                                             if runner.fused else "z-slabs + NCCL field all-gather"))
                            if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
                            "time_seed": "step index", "initial_field": "zero"},
                 "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"],

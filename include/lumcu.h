@@ -125,6 +125,14 @@ int lumcu_peers_open(LumcuCtx *ctx, int32_t rank, int32_t nranks, const uint8_t 
 int lumcu_peers_close(LumcuCtx *ctx);
 int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift,
                                int32_t z_begin, int32_t z_end);
+/* Interleaved probe sharding: the dispatch's workgroups are cut into chunks of 3072 and shard `rank` of `nranks`
+ * takes chunks rank, rank + nranks, ...  Unlike z-slabs this balances the ranks whatever the scene looks like
+ * (every rank samples every part of the world); it needs the texel-wise exchange, since a shard's texels are
+ * not contiguous in the field.  lumcu_update_shard: trace + local commit of one shard (the union over all
+ * shards, each from the same starting field, equals lumcu_update).  lumcu_update_shard_exchange: the per-frame
+ * call of step 4 above with this sharding (rank and nranks as given to lumcu_peers_open). */
+int lumcu_update_shard(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift, int32_t rank, int32_t nranks);
+int lumcu_update_shard_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift);
 
 /* shift_radiance (internal_render.cpp:1218-1335): field[p] = field[p + d] over the overlap box. */
 int lumcu_shift(LumcuCtx *ctx, int32_t dx, int32_t dy, int32_t dz);

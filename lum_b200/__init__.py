@@ -60,6 +60,8 @@ SYMBOLS = {
     "lumcu_peers_open": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "lumcu_peers_close": (C.c_int, [_P]),
     "lumcu_update_slab_exchange": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_update_shard": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "lumcu_update_shard_exchange": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "lumcu_upload_model": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "lumcu_free_model": (C.c_int, [_P, C.c_int32]),
     "lumcu_copy_bricks": (C.c_int, [_P, _P, _P, C.c_int32]),
@@ -224,6 +226,12 @@ class RadianceStage:
         v = self.glossy_view(view)
         self._ck(self.lib.lumcu_glossy(self.ctx, C.byref(v), w, h, _ptr(mn), _ptr(dp), _ptr(fr), _ptr(cov)))
         return fr, cov
+
+    def update_shard(self, time_seed, size, shift, rank, nranks):
+        self._ck(self.lib.lumcu_update_shard(self.ctx, int(time_seed), int(size), int(shift), int(rank), int(nranks)))
+
+    def update_shard_exchange(self, time_seed, size=1, shift=0):
+        self._ck(self.lib.lumcu_update_shard_exchange(self.ctx, int(time_seed), int(size), int(shift)))
 
     def shift(self, dx, dy, dz):
         self._ck(self.lib.lumcu_shift(self.ctx, int(dx), int(dy), int(dz)))

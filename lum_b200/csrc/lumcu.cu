@@ -126,6 +126,7 @@ struct LumcuCtx {
     unsigned long long *d_totals = nullptr;
     long long dbg_nwg = 0;       // workgroups of the last instrumented update
     long long dbg_wg_begin = 0;
+    long long dbg_traced = 0;    // workgroups the last instrumented update traced (totals[2])
 
     // models (map.comp inputs) and blockify copy pairs
     struct Model { uint8_t *d_vox = nullptr; int sx = 0, sy = 0, sz = 0; };
@@ -201,17 +202,19 @@ int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long 
 
 template <bool DEBUG>
 int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
+    // 3 ray slots per thread everywhere (what the R = 64 sweep found best: the slots compete with L1 for the SM's
+    // 256 KB); a batch must hold whole probes, so R = 256 takes 256 threads (3 probes per CTA)
     switch (c->R) {
-        case 16: return launch_pool_one<16, 256, 4, DEBUG>(c, sv, a, nwg);
-        case 32: return launch_pool_one<32, 256, 4, DEBUG>(c, sv, a, nwg);
+        case 16: return launch_pool_one<16, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
+        case 32: return launch_pool_one<32, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
 #ifdef LUMCU_T64
         case 64: return launch_pool_one<64, 64, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
 #else
         case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg)
-                                               : launch_pool_one<64, 256, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
+                                               : launch_pool_one<64, 256, 4, DEBUG>(c, sv, a, nwg);
 #endif
-        case 128: return launch_pool_one<128, 256, 4, DEBUG>(c, sv, a, nwg);
-        case 256: return launch_pool_one<256, 256, 4, DEBUG>(c, sv, a, nwg);
+        case 128: return launch_pool_one<128, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
+        case 256: return launch_pool_one<256, 256, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);
     }
 }
@@ -264,8 +267,17 @@ SceneView scene_view(LumcuCtx *c) {
                      c->brick0_empty ? 1 : 0, c->d_scene_flags};
 }
 
+// Interleaved sharding (UpdateArgs::il_*): chunk is a multiple of every pooled kernel's probes-per-CTA.
+constexpr int IL_CHUNK = 3072;
+// number of workgroups of [0, total) that shard `il` owns
+long long il_count(long long total, const Interleave &il) {
+    if (il.n <= 1) return total;
+    const long long full = total / il.chunk, rem = total % il.chunk;
+    return (full / il.n) * il.chunk + ((full % il.n) > il.rank ? il.chunk : 0) + ((full % il.n) == il.rank ? rem : 0);
+}
+
 int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begin, long long wg_end,
-              int z_begin, int z_end, bool commit = true) {
+              int z_begin, int z_end, bool commit = true, Interleave il = Interleave{IL_CHUNK, 0, 1}) {
     if (!c->have_world || !c->have_bricks || !c->have_materials)
         return fail(LUMCU_E_STATE, "lumcu_update before world/bricks/materials were uploaded");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
@@ -273,7 +285,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
     const long long nwg_all = c->nreq / size;
     if (wg_begin < 0 || wg_end > nwg_all || wg_begin > wg_end)
         return fail(LUMCU_E_ARG, "workgroup range [%lld,%lld) outside [0,%lld)", wg_begin, wg_end, nwg_all);
-    const long long nwg = wg_end - wg_begin;
+    const long long nwg = il_count(wg_end - wg_begin, il);     // workgroups this launch traces
     if (nwg > 0) {
         if (int rc = ensure_validated(c)) return rc;
         const SceneView sv = scene_view(c);
@@ -282,6 +294,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         a.dir_table = c->d_table;
         a.staged = c->d_staged;
         a.wg_begin = wg_begin; a.wg_end = wg_end;
+        a.il_chunk = il.chunk; a.il_rank = il.rank; a.il_n = il.n;
         a.time_seed = time_seed; a.size = size; a.shift = shift;
         a.z_begin = z_begin; a.z_end = z_end;
         a.reactiveness = c->desc.reactiveness;
@@ -298,7 +311,8 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             a.dbg_totals = c->d_totals;
             CU(cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
             if (int rc = (use_pool ? launch_update_pool<true>(c, sv, a, nwg) : launch_update_R<true>(c, sv, a, nwg))) return rc;
-            c->dbg_nwg = nwg; c->dbg_wg_begin = wg_begin;
+            c->dbg_traced = nwg;
+            c->dbg_nwg = il.n > 1 ? wg_end - wg_begin : nwg; c->dbg_wg_begin = wg_begin;   // (a shard leaves the other ranks' entries untouched)
         } else {
             if (c->profiling) CU(cudaEventRecord(c->ev_k0, c->stream));
             if (int rc = (use_pool ? launch_update_pool<false>(c, sv, a, nwg) : launch_update_R<false>(c, sv, a, nwg))) return rc;
@@ -307,7 +321,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         if (commit) {
             const int ct = 256;
             commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
-                c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end);
+                c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il);
             c->launches++;
             CU(cudaGetLastError());
         }
@@ -315,12 +329,13 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
     return 0;
 }
 
-int commit_to_peers(LumcuCtx *c, int size, int shift, long long wg_begin, long long wg_end, int z_begin, int z_end) {
-    const long long nwg = wg_end - wg_begin;
+int commit_to_peers(LumcuCtx *c, int size, int shift, long long wg_begin, long long wg_end, int z_begin, int z_end,
+                    Interleave il = Interleave{IL_CHUNK, 0, 1}) {
+    const long long nwg = il_count(wg_end - wg_begin, il);
     if (nwg <= 0) return 0;
     const int ct = 256;
     commit_peers_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
-        c->peer_fields, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end);
+        c->peer_fields, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -793,6 +808,35 @@ int lumcu_peers_open(LumcuCtx *c, int32_t rank, int32_t nranks, const uint8_t *h
     return 0;
 }
 
+int lumcu_update_shard(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t rank, int32_t nranks) {
+    if (int rc = use(c)) return rc;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LUMCU_E_ARG, "bad shard %d of %d", rank, nranks);
+    if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, Interleave{IL_CHUNK, rank, nranks})) return rc;
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+int lumcu_update_shard_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift) {
+    if (int rc = use(c)) return rc;
+    if (!c->have_peers) return fail(LUMCU_E_STATE, "lumcu_update_shard_exchange before lumcu_peers_open");
+    if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
+    if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
+    const Interleave il{IL_CHUNK, c->peer_rank, c->peer_n};
+    const long long nwg_all = c->nreq / size;
+    c->epoch++;
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, 0, nwg_all, -32768, 32768, false, il)) return rc;
+    if (int rc = peer_barrier(c, 0)) return rc;             // every rank has finished reading its field
+    if (int rc = commit_to_peers(c, size, shift, 0, nwg_all, -32768, 32768, il)) return rc;
+    if (int rc = peer_barrier(c, 1)) return rc;             // every rank's texels have landed everywhere
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
 int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
     if (int rc = use(c)) return rc;
     if (!c->have_peers) return fail(LUMCU_E_STATE, "lumcu_update_slab_exchange before lumcu_peers_open");
@@ -870,7 +914,7 @@ int lumcu_download_debug(LumcuCtx *c, float *pre_blend, uint32_t *ray_samples, u
     unsigned long long t[2] = {0, 0};
     CU(cudaMemcpyAsync(t, c->d_totals, sizeof t, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (totals) { totals[0] = t[0]; totals[1] = t[1]; totals[2] = (uint64_t)n; }
+    if (totals) { totals[0] = t[0]; totals[1] = t[1]; totals[2] = (uint64_t)c->dbg_traced; }
     return 0;
 }
 

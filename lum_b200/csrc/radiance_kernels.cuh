@@ -14,11 +14,22 @@ struct UpdateArgs {
     unsigned long long *__restrict__ dbg_totals;  // S, H
     long long wg_begin;                    // first workgroup of this launch
     long long wg_end;
+    // Interleaved probe sharding (multi-GPU): the range is cut into chunks of il_chunk workgroups and this launch
+    // takes chunks il_rank, il_rank + il_n, ...  il_n == 1: the whole range.  (Every rank then samples every
+    // part of the world, which balances ranks whatever the scene looks like; z-slabs only balance uniform ones.)
+    int il_chunk, il_rank, il_n;
     int time_seed, size, shift;
     int z_begin, z_end;                    // only probes with z in [z_begin,z_end) are processed
     float reactiveness;
     float sun_x, sun_y, sun_z;
 };
+
+// i-th workgroup of this launch -> workgroup index of the dispatch (see UpdateArgs::il_*)
+__device__ __forceinline__ long long il_map(long long wg_begin, int il_chunk, int il_rank, int il_n, long long i) {
+    if (il_n <= 1) return wg_begin + i;
+    const long long c = i / il_chunk;
+    return wg_begin + (c * il_n + il_rank) * il_chunk + (i - c * il_chunk);
+}
 
 // One CTA = one workgroup of radiance.comp (radiance.comp:360-414): R threads, one ray each.
 // The subgroup reduction is the xor butterfly the oracle pins; _light[] lives in shared memory.
@@ -28,7 +39,8 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
     constexpr int NSUB = R / SUB;
     __shared__ float sh_light[NSUB][3];
 
-    const long long w = a.wg_begin + (long long)blockIdx.x;
+    const long long w = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x);
+    if (w >= a.wg_end) return;                                   // uniform per CTA (tail of an interleaved shard)
     const int ray = threadIdx.x;
     const short4 rq = a.requests[w * (long long)a.size + a.shift];
     if (rq.z < a.z_begin || rq.z >= a.z_end) return;          // uniform per CTA
@@ -177,7 +189,8 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                     if (cur >= 0) {
                         dst[base + __popc(~idle & ((1u << lane) - 1u))] = (unsigned short)cur;
                         sm.a[cur].w = q.t;
-                        sm.done[cur] = 0;
+                        if constexpr (PRIVATE) sm.done[cur] = 0;   // pass 0 only: in the tail passes it already is 0, and the
+                                                                    // other warps are reading done[] by then (phase C)
                         if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                     }
                     break;
@@ -255,8 +268,9 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     int &sm_next = cta.next, &sm_chunk = cta.chunk;
     int (&sm_park)[3] = cta.park;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long wg0 = a.wg_begin + (long long)blockIdx.x * PPC;
+    const long long wg0 = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x * PPC);   // il_chunk % PPC == 0
     const long long left = a.wg_end - wg0;
+    if (left <= 0) return;                                       // uniform per CTA (tail of an interleaved shard)
     const int nprobes = left < PPC ? (int)left : PPC;
     const int nrays = nprobes * R;
     for (int i = tid; i < nprobes; i += THREADS) sm_req[i] = a.requests[(wg0 + i) * (long long)a.size + a.shift];
@@ -399,10 +413,11 @@ __global__ void validate_world_kernel(const int16_t *__restrict__ world, long lo
 
 // Deferred imageStore (radiance.comp:353): scatter the staged texels of workgroups
 // [wg_begin, wg_end) into the field once every read of the old field is done.
+struct Interleave { int chunk, rank, n; };
 __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__restrict__ staged,
                               const short4 *__restrict__ requests, long long wg_begin, long long wg_end,
-                              int size, int shift, int wx, int wy, int wz, int z_begin, int z_end) {
-    long long w = wg_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                              int size, int shift, int wx, int wy, int wz, int z_begin, int z_end, Interleave il) {
+    long long w = il_map(wg_begin, il.chunk, il.rank, il.n, (long long)blockIdx.x * blockDim.x + threadIdx.x);
     if (w >= wg_end) return;
     short4 rq = requests[w * (long long)size + shift];
     if (rq.z < z_begin || rq.z >= z_end) return;
@@ -420,8 +435,8 @@ struct PeerFlags { unsigned *f[MAX_PEERS]; int n; int rank; };
 
 __global__ void commit_peers_kernel(PeerFields pf, const uint32_t *__restrict__ staged,
                                     const short4 *__restrict__ requests, long long wg_begin, long long wg_end,
-                                    int size, int shift, int wx, int wy, int wz, int z_begin, int z_end) {
-    long long w = wg_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                    int size, int shift, int wx, int wy, int wz, int z_begin, int z_end, Interleave il) {
+    long long w = il_map(wg_begin, il.chunk, il.rank, il.n, (long long)blockIdx.x * blockDim.x + threadIdx.x);
     if (w >= wg_end) return;
     short4 rq = requests[w * (long long)size + shift];
     if (rq.z < z_begin || rq.z >= z_end) return;

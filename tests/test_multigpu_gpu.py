@@ -45,6 +45,13 @@ for f in range(4):
 out = st.download_field()
 dist.barrier()
 np.save(os.path.join(os.environ["OUT_DIR"], f"g{rank}.npy"), out)
+# and with interleaved shards instead of z-slabs (same peer set)
+st.upload_field(np.zeros(st.cells, np.uint32)); st.wait_idle(); dist.barrier()
+for f in range(4):
+    st.update_shard_exchange(f, 1, 0)
+out = st.download_field()
+dist.barrier()
+np.save(os.path.join(os.environ["OUT_DIR"], f"h{rank}.npy"), out)
 st.peers_close()
 dist.barrier(); dist.destroy_process_group()
 '''
@@ -75,6 +82,8 @@ def test_two_gpu_slabs_match_single_gpu(tmp_path):
     assert np.array_equal(a, ref)
     ga, gb = np.load(tmp_path / "g0.npy"), np.load(tmp_path / "g1.npy")
     assert np.array_equal(ga, ref) and np.array_equal(gb, ref)        # fused exchange: same bits
+    ha, hb = np.load(tmp_path / "h0.npy"), np.load(tmp_path / "h1.npy")
+    assert np.array_equal(ha, ref) and np.array_equal(hb, ref)        # interleaved shards: same bits
 
 
 def test_peer_exchange_single_rank_degenerates_to_update(oracle_mod, demo):

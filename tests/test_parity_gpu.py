@@ -317,6 +317,36 @@ def test_ranges_and_slabs_compose(oracle_mod, demo):
     assert st.slab_range(1, 0, 4, 8) == (int(np.searchsorted(zs[:prefix], 4)), int(np.searchsorted(zs[:prefix], 8)))
 
 
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_interleaved_shards_compose(oracle_mod, nranks):
+    """lumcu_update_shard: chunks of 3072 workgroups dealt round-robin to the ranks.  Each shard, run from the
+    same starting field, must change exactly its own probes' texels to the oracle's values; together they make
+    the full update.  The world is large enough for several chunks per rank and a ragged last chunk, and for
+    the pooled kernel (>= 2^19 rays per shard at 2 ranks) as well as the per-workgroup one."""
+    O = oracle_mod
+    scn = scenes.synthetic_scene(40, 36, 16, palette=48, seed=21)
+    st = make_stage(scn)
+    sc = oracle_scene(O, scn)
+    n = st.build_requests(np.array([(1, 2, 3, 0), (30, 30, 15, 0)], np.int16))
+    req = st.download_requests()
+    assert n > 6 * 3072 and n % 3072 != 0
+    rng = np.random.default_rng(nranks)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 5)["field"]
+    cell = req[:, 0].astype(np.int64) + 40 * (req[:, 1].astype(np.int64) + 36 * req[:, 2].astype(np.int64))
+    owner = (np.arange(n) // 3072) % nranks
+    union = f0.copy()
+    for r in range(nranks):
+        st.upload_field(f0)
+        st.update_shard(5, 1, 0, r, nranks)
+        got = st.download_field()
+        mine = np.zeros(sc.cells, bool); mine[cell[owner == r]] = True
+        assert np.array_equal(got[mine], ref[mine]), r
+        assert np.array_equal(got[~mine], f0[~mine]), r
+        union[mine] = got[mine]
+    assert np.array_equal(union, ref)
+
+
 def test_shift_matches_oracle(oracle_mod, demo):
     O = oracle_mod
     st = make_stage(demo)
