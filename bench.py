@@ -170,6 +170,20 @@ class Runner:
             D.open_peer_exchange(self.st, rank, world_size, device=f"cuda:{device}")
             self.fused = True
 
+    def close(self):
+        """Tear down in an order torch can live with: the pinned buffers were used on the stage's stream (an
+        ExternalStream), and torch's host allocator records an event on that stream when they are freed -- so they
+        must go while the stream still exists, i.e. before lumcu_destroy."""
+        self.torch.cuda.synchronize()
+        if self.fused:
+            self.st.peers_close()
+            self.fused = False
+        self.world_host = self.field_host = None
+        self._pin_w = self._pin_f = None
+        self.field_t = self.flush = None
+        self.torch.cuda.synchronize()
+        self.st.close()
+
     def flush_l2(self, k=0):
         with self.torch.cuda.stream(self.stream):
             self.flush.fill_(k & 0xFF)
@@ -494,6 +508,7 @@ def run_ours(args, rank, local_rank, world_size):
     if rank == 0 and world_size == 1 and args.workload != "demo" and not args.no_demo:
         dr = Runner(make_scene("demo"), local_rank, 0, 1, torch, dist)
         dm = measure(dr, max(args.steps, 20), max(args.warmup, 5), peak)
+        dr.close()
         try:     # in a child process: the API mirror abort()s on errors (reference behaviour) and must not take the bench down
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--api-config3"], capture_output=True,
                                text=True, timeout=300, env=dict(os.environ, LUM_B200_DEVICE=str(local_rank)))
@@ -536,6 +551,9 @@ def run_ours(args, rank, local_rank, world_size):
             line["cpu_baseline"] = cb
         line.update(extra)
         print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.barrier()                  # nobody unmaps a peer's field while another rank may still store into it
+    runner.close()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
