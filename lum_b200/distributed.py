@@ -7,10 +7,30 @@ words), updates exactly the probes of that slab (lumcu_update_slab) and then all
 their slabs -- either with ONE in-place all-gather (all_gather_field), or fused into the commit itself:
 lumcu_update_slab_exchange stores every new texel straight into all ranks' field replicas over NVLink
 peer memory between two flag barriers (open_peer_exchange wires it) -- after which every rank holds the
-identical new field for the next frame's gathers.  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
+identical new field for the next frame's gathers.  With the fused exchange a rank's texels need not be contiguous
+in the field, so the default sharding there is INTERLEAVED (lumcu_update_shard_exchange): the dispatch's
+workgroups are dealt to the ranks in chunks of SHARD_CHUNK, which balances the ranks whatever the scene looks
+like (z-slabs only balance uniform scenes; the demo world is all ground).  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
 CPU for the tests of this host-side logic).
 """
 from __future__ import annotations
+
+
+SHARD_CHUNK = 3072      # = IL_CHUNK of csrc/lumcu.cu: a multiple of every pooled kernel's probes per CTA
+
+
+def shard_workgroups(nwg: int, rank: int, world_size: int, chunk: int = SHARD_CHUNK):
+    """Workgroup indices of [0, nwg) that interleaved shard `rank` of `world_size` owns, in the order the
+    kernels visit them: chunk c of the dispatch belongs to rank c % world_size (lumcu_update_shard)."""
+    import numpy as np
+    w = np.arange(nwg, dtype=np.int64)
+    return w[(w // chunk) % world_size == rank]
+
+
+def shard_count(nwg: int, rank: int, world_size: int, chunk: int = SHARD_CHUNK) -> int:
+    """len(shard_workgroups(...)) in closed form (what sizes the shard's launches)."""
+    full, rem = divmod(nwg, chunk)
+    return (full // world_size) * chunk + (chunk if full % world_size > rank else 0) + (rem if full % world_size == rank else 0)
 
 
 def slab_bounds(wz: int, rank: int, world_size: int):

@@ -26,6 +26,22 @@ def test_slab_arithmetic():
     assert cover == list(range(64))
 
 
+@pytest.mark.parametrize("nwg", [0, 1, 3071, 3072, 3073, 6 * 3072 + 17, 100000])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_interleaved_shard_arithmetic(nwg, world):
+    """The shards partition the dispatch, and the closed-form count (the one the launches are sized with)
+    agrees with the enumeration."""
+    seen = np.zeros(nwg, np.int32)
+    for r in range(world):
+        idx = D.shard_workgroups(nwg, r, world)
+        assert len(idx) == D.shard_count(nwg, r, world)
+        assert np.all(np.diff(idx) > 0)
+        seen[idx] += 1
+    assert np.all(seen == 1)
+    sizes = [D.shard_count(nwg, r, world) for r in range(world)]
+    assert max(sizes) - min(sizes) <= D.SHARD_CHUNK
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -80,3 +96,48 @@ def test_two_rank_gloo_matches_single_rank(tmp_path):
     b = np.load(tmp_path / "field_1.npy")
     assert np.array_equal(a, b)          # every rank ends with the identical field
     assert np.array_equal(a, f)          # and it is the single-rank result
+
+
+def _shard_worker(rank, world, port, frames, out_dir):
+    """Interleaved shards + a texel-wise exchange (what commit_peers_kernel does with peer stores, here as an
+    all_gather of (cell, word) pairs).  A small chunk makes the demo's 2,692 workgroups span several chunks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    d = scenes.demo_scene()
+    sc = O.Scene(d["world"], d["bricks"], d["materials"])
+    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16)
+    req = O.build_requests(d["world"], sp)
+    mine = D.shard_workgroups(len(req), rank, world, chunk=384)
+    cell = req[:, 0].astype(np.int64) + sc.wx * (req[:, 1].astype(np.int64) + sc.wy * req[:, 2].astype(np.int64))
+    field = np.zeros(sc.cells, np.uint32)
+    for f in range(frames):
+        new = field.copy()
+        runs = np.split(mine, np.nonzero(np.diff(mine) != 1)[0] + 1) if len(mine) else []
+        for run in runs:
+            r = O.update(sc, field, req, f, wg_range=(int(run[0]), int(run[-1]) + 1), nthreads=2)
+            new[cell[run]] = r["field"][cell[run]]
+        pairs = [None] * world
+        dist.all_gather_object(pairs, (cell[mine], new[cell[mine]]))
+        for c, w in pairs:
+            field[c] = w
+    np.save(os.path.join(out_dir, f"shard_{rank}.npy"), field)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_interleaved_shards_match_single_rank(tmp_path):
+    import oracle as O
+    frames = 3
+    port = _free_port()
+    mp.spawn(_shard_worker, args=(2, port, frames, str(tmp_path)), nprocs=2, join=True)
+    d = scenes.demo_scene()
+    sc = O.Scene(d["world"], d["bricks"], d["materials"])
+    req = O.build_requests(d["world"], np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16))
+    f = np.zeros(sc.cells, np.uint32)
+    for k in range(frames):
+        f = O.update(sc, f, req, k)["field"]
+    a, b = np.load(tmp_path / "shard_0.npy"), np.load(tmp_path / "shard_1.npy")
+    assert np.array_equal(a, b) and np.array_equal(a, f)

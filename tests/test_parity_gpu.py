@@ -334,7 +334,10 @@ def test_interleaved_shards_compose(oracle_mod, nranks):
     f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
     ref = O.update(sc, f0, req, 5)["field"]
     cell = req[:, 0].astype(np.int64) + 40 * (req[:, 1].astype(np.int64) + 36 * req[:, 2].astype(np.int64))
-    owner = (np.arange(n) // 3072) % nranks
+    from lum_b200 import distributed as D
+    owner = np.empty(n, np.int64)
+    for r in range(nranks):
+        owner[D.shard_workgroups(n, r, nranks)] = r
     union = f0.copy()
     for r in range(nranks):
         st.upload_field(f0)
