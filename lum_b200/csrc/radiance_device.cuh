@@ -164,6 +164,19 @@ __device__ __forceinline__ int march_step(const SceneView &s, const MarchConsts 
     return voxel != 0 ? 1 : ((out || !(t < 128.0f)) ? 2 : 0);   // !(t<128): a NaN fraction ends the ray (decree 13)
 }
 
+// 16*b + c as ONE multiply-add on the FMA pipe (left to itself the compiler re-derives 16*b as `i & ~15` on the
+// ALU pipe, the one this loop is short of, and adds separately).
+__device__ __forceinline__ int mad16(int b, int c) {
+    int r;
+    asm("mad.lo.s32 %0, %1, 16, %2;" : "=r"(r) : "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int msub16(int b, int c) {     // c - 16*b
+    int r;
+    asm("mad.lo.s32 %0, %1, -16, %2;" : "=r"(r) : "r"(b), "r"(c));
+    return r;
+}
+
 // ---- the same iteration for the validated device mirror -----------------------------------
 // Preconditions (checked on the device, see SceneView::flags): brick 0 is empty and every world id is
 // in [0, capacity).  Differences from march_step, none of which can change a result:
@@ -192,13 +205,13 @@ __device__ __forceinline__ bool march_step_fast(const SceneView &s, const uint3 
     int id = 0;
     if (!out) id = __ldg(wp);
     // ((ix&15)<<8 | (iy&15)<<4 | iz&15) == V - 16*B with V = (ix*16+iy)*16+iz, B = (bx*16+by)*16+bz
-    const int V = (ix * 16 + iy) * 16 + iz, B = (bx * 16 + by) * 16 + bz;
-    const uint8_t *bp = s.bricks + (uint32_t)(id * 4096 + (V - 16 * B));
+    const int V = mad16(mad16(ix, iy), iz), B = mad16(mad16(bx, by), bz);
+    const uint8_t *bp = s.bricks + (uint32_t)(id * 4096 + msub16(B, V));
     int voxel = 0;
     if (id != 0) voxel = __ldg(bp);
-    const float cx = __int_as_float(bx * 16 + cm.x) - 8388608.0f;
-    const float cy = __int_as_float(by * 16 + cm.y) - 8388608.0f;
-    const float cz = __int_as_float(bz * 16 + cm.z) - 8388608.0f;
+    const float cx = __int_as_float(mad16(bx, cm.x)) - 8388608.0f;
+    const float cy = __int_as_float(mad16(by, cm.y)) - 8388608.0f;
+    const float cz = __int_as_float(mad16(bz, cm.z)) - 8388608.0f;
     const float ex = cx * inv.x + (-px * inv.x);
     const float ey = cy * inv.y + (-py * inv.y);
     const float ez = cz * inv.z + (-pz * inv.z);
