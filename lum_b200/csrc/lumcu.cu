@@ -302,7 +302,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         // the z filter (unsorted special tail of a slab update) only exists in the per-workgroup kernel
         // and small dispatches (demo-sized worlds) are latency-bound: they want one workgroup per CTA
         const bool unfiltered = z_begin <= -32768 && z_end >= 32768;
-        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && nwg * c->R >= (1ll << 19)));
+        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && nwg * c->R >= (1ll << 23)));
         if (c->debug_flags) {
             if (int rc = ensure_debug(c)) return rc;
             a.dbg_pre_blend = (c->debug_flags & LUMCU_DEBUG_PRE_BLEND) ? c->d_pre_blend : nullptr;

@@ -365,7 +365,9 @@ __device__ __forceinline__ bool march_ray(const SceneView &s, const MarchConsts 
     return st == 1;
 }
 
-// Whole ray, one thread (the one-workgroup-per-CTA kernel).
+// Whole ray, one thread (the one-workgroup-per-CTA kernel).  VALID: the scene passed validation, so the fast
+// march and the in-world fetches apply (see march_step_fast).
+template <bool VALID>
 __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px, int py, int pz,
                                                      uint32_t gid_x, int ray, f3 fib, int time_seed,
                                                      f3 sun) {
@@ -373,13 +375,25 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
     setup_ray(px, py, pz, gid_x, ray, fib, time_seed, o, d, inv);
     const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
     float t = 0.0f;
-    int samples = 0, st;
-    do { st = march_step(s, mc, o, d, inv, t); samples++; } while (st == 0);
+    int samples = 0;
+    bool hit;
+    if constexpr (VALID) {
+        const uint3 wsbits = {__float_as_uint(mc.wsx), __float_as_uint(mc.wsy), __float_as_uint(mc.wsz)};
+        const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
+        float t_pre;
+        bool done;
+        do { done = march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit); samples++; } while (!done);
+        if (!hit && resolve_pending(s, mc, o, d, t_pre)) { hit = true; t = t_pre; }
+    } else {
+        int st;
+        do { st = march_step(s, mc, o, d, inv, t); samples++; } while (st == 0);
+        hit = st == 1;
+    }
     __syncwarp();   // reconverge before the long tail (early leavers would run it in separate passes)
     RayResult res;
     int nr;
-    res.light = finish_ray<false>(s, o, d, inv, t, st == 1, sun, nr);
-    res.hit = st == 1;
+    res.light = finish_ray<VALID>(s, o, d, inv, t, hit, sun, nr);
+    res.hit = hit;
     res.samples = samples + nr;
     return res;
 }

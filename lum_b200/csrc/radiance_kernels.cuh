@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
     const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
     const f3 sun = {a.sun_x, a.sun_y, a.sun_z};
 
-    RayResult r = trace_probe_ray(s, rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, sun);
+    const bool valid = s.brick0_empty && !(__ldg(s.flags) & 1u);        // uniform
+    RayResult r = valid ? trace_probe_ray<true>(s, rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, sun)
+                        : trace_probe_ray<false>(s, rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, sun);
 
     float lx = r.light.x, ly = r.light.y, lz = r.light.z;
     constexpr unsigned mask = SUB == 32 ? 0xffffffffu : ((1u << SUB) - 1u);

@@ -322,7 +322,8 @@ def test_interleaved_shards_compose(oracle_mod, nranks):
     """lumcu_update_shard: chunks of 3072 workgroups dealt round-robin to the ranks.  Each shard, run from the
     same starting field, must change exactly its own probes' texels to the oracle's values; together they make
     the full update.  The world is large enough for several chunks per rank and a ragged last chunk, and for
-    the pooled kernel (>= 2^19 rays per shard at 2 ranks) as well as the per-workgroup one."""
+    the per-workgroup kernel that auto-selection takes at this size (the pooled kernel is covered by variant 1 in
+    assert_update_equal and, with interleaving, by the 2-GPU test and the bench)."""
     O = oracle_mod
     scn = scenes.synthetic_scene(40, 36, 16, palette=48, seed=21)
     st = make_stage(scn)
