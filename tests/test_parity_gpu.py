@@ -322,8 +322,7 @@ def test_interleaved_shards_compose(oracle_mod, nranks):
     """lumcu_update_shard: chunks of 3072 workgroups dealt round-robin to the ranks.  Each shard, run from the
     same starting field, must change exactly its own probes' texels to the oracle's values; together they make
     the full update.  The world is large enough for several chunks per rank and a ragged last chunk, and for
-    the per-workgroup kernel that auto-selection takes at this size (the pooled kernel is covered by variant 1 in
-    assert_update_equal and, with interleaving, by the 2-GPU test and the bench)."""
+    both kernels."""
     O = oracle_mod
     scn = scenes.synthetic_scene(40, 36, 16, palette=48, seed=21)
     st = make_stage(scn)
@@ -339,16 +338,18 @@ def test_interleaved_shards_compose(oracle_mod, nranks):
     owner = np.empty(n, np.int64)
     for r in range(nranks):
         owner[D.shard_workgroups(n, r, nranks)] = r
-    union = f0.copy()
-    for r in range(nranks):
-        st.upload_field(f0)
-        st.update_shard(5, 1, 0, r, nranks)
-        got = st.download_field()
-        mine = np.zeros(sc.cells, bool); mine[cell[owner == r]] = True
-        assert np.array_equal(got[mine], ref[mine]), r
-        assert np.array_equal(got[~mine], f0[~mine]), r
-        union[mine] = got[mine]
-    assert np.array_equal(union, ref)
+    for variant in (1, 0):                     # pooled and per-workgroup kernel: both map launch index -> workgroup
+        st.set_kernel_variant(variant)
+        union = f0.copy()
+        for r in range(nranks):
+            st.upload_field(f0)
+            st.update_shard(5, 1, 0, r, nranks)
+            got = st.download_field()
+            mine = np.zeros(sc.cells, bool); mine[cell[owner == r]] = True
+            assert np.array_equal(got[mine], ref[mine]), (variant, r)
+            assert np.array_equal(got[~mine], f0[~mine]), (variant, r)
+            union[mine] = got[mine]
+        assert np.array_equal(union, ref), variant
 
 
 def test_shift_matches_oracle(oracle_mod, demo):
