@@ -70,8 +70,17 @@ __device__ __forceinline__ float unorm10_to_float(uint32_t c) {
     const float fc = (float)c;
     return __fmaf_rn(fc, r, fc * rl);
 }
+// The G and B fields are converted where they sit: float(w & (1023 << k)) = c * 2^k exactly (10 significant
+// bits), and scaling r and rl by 2^-k is exact too, so the same fma yields the same bits without the shift.
+template <int K>
+__device__ __forceinline__ float unorm10_field(uint32_t w) {
+    const float r = __uint_as_float(0x3a802008u - ((uint32_t)K << 23));     // RN(1/1023) * 2^-K
+    const float rl = __uint_as_float(0x2b802008u - ((uint32_t)K << 23));    // RN(1/1023 - r) * 2^-K
+    const float f = (float)(w & (1023u << K));
+    return __fmaf_rn(f, r, f * rl);
+}
 __device__ __forceinline__ f3 unpack10(uint32_t w) {
-    return {unorm10_to_float(w & 1023u), unorm10_to_float((w >> 10) & 1023u), unorm10_to_float((w >> 20) & 1023u)};
+    return {unorm10_field<0>(w), unorm10_field<10>(w), unorm10_field<20>(w)};
 }
 __device__ __forceinline__ uint32_t unorm10(float v) {
     float c = gmin(gmax(v, 0.0f), 1.0f);
