@@ -179,7 +179,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                     }
                 }
                 exhausted = base + cnt >= limit;
-                idle = __ballot_sync(FULL, cur < 0);
+                if (exhausted) idle = __ballot_sync(FULL, cur < 0);   // otherwise every idle lane got a ray
             }
             if (exhausted) {
                 const int act = 32 - __popc(idle);
@@ -239,6 +239,9 @@ __device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const Scen
     }
 }
 
+#ifndef LUMCU_TAILDIV
+#define LUMCU_TAILDIV 48       // stragglers per tail warp
+#endif
 #ifndef LUMCU_PARK
 #define LUMCU_PARK 8          // tuned on B200 (C4 world): 8 beats 1/4/16/24/32
 #endif
@@ -303,7 +306,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     }
     __syncthreads();
     const int parked0 = sm_park[0];
-    const int tail_warps = parked0 == 0 ? 0 : max(1, min(NW, (parked0 + 47) / 48));
+    const int tail_warps = parked0 == 0 ? 0 : max(1, min(NW, (parked0 + LUMCU_TAILDIV - 1) / LUMCU_TAILDIV));
     const int tail_threads = tail_warps * 32;
 
     // ---- phase B': the tail warps march the stragglers among themselves ----
@@ -313,7 +316,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
             const int wr = rd == 1 ? 2 : 1;
             if (tid == 0) { sm_next = 0; sm_park[wr] = 0; }
             asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
-            const int parts = max(1, min(tail_warps, (limit + 47) / 48));
+            const int parts = max(1, min(tail_warps, (limit + LUMCU_TAILDIV - 1) / LUMCU_TAILDIV));
             if (warp < parts)
                 pool_march<NR, PARK, DEBUG, false, FAST>(sm, s, mc, &sm_next, 0, sm_list[rd], limit, sm_list[wr], &sm_park[wr], parts > 1, lane);
             asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
