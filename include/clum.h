@@ -120,6 +120,12 @@ int lum_b200_get_frame_index(const LumRenderer instance);
 /* Radiance field, A2B10G10R10 words, index x + X*(y + Y*z): world_size cells. */
 void lum_b200_download_radiance_field(LumRenderer instance, uint32_t* words);
 void lum_b200_upload_radiance_field(LumRenderer instance, const uint32_t* words);
+/* The glossy pass (shaders/glossy.frag; LumInternalRenderer::glossy, internal_render.cpp:2027-2037) over a
+ * caller-supplied G-buffer, with the renderer's camera (lum_b200_set_camera) and light direction: mat_norm
+ * uint8 [h][w][4] (R8G8B8A8_UINT: material, normal), depth float [h][w] in [0,1]; frame float [h][w][4] receives
+ * the fragment colour (before the blend) where covered (uint8 [h][w], may be NULL) is 1.  See lumcu_glossy. */
+void lum_b200_glossy(LumRenderer instance, int width, int height, const uint8_t* mat_norm, const float* depth,
+                     float* frame, uint8_t* covered);
 /* Device block palette (bricks [first, first+count), BlockVoxels layout) and world ids as the
  * radiance kernel sees them after the last submitted frame. */
 void lum_b200_download_block_palette(LumRenderer instance, int first, int count, uint8_t* voxels);

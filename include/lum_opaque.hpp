@@ -129,6 +129,10 @@ public:
     // host-side consumers / tests (the reference never reads these back)
     void download_radiance_field(uint32_t* words);       // world cells, x + X*(y + Y*z)
     void upload_radiance_field(const uint32_t* words);
+    // glossy() (internal_render.cpp:2027-2037) as a compute pass over a caller-supplied G-buffer; the uniform block is
+    // filled from `camera` and `lightDir` as start_raygen does (:1580-1592).  frame: RGBA f32, written where covered.
+    dvec3 lightDir = dvec3(0.4368520327, 0.4368520327, -0.7863336589);   // normalize(0.5, 0.5, -0.9), internal_render.hpp:259
+    void glossy(int width, int height, const uint8_t* mat_norm, const float* depth, float* frame, uint8_t* covered);
     void download_block_palette(int first, int count, uint8_t* voxels);
     void download_world(int16_t* ids);
     void wait_idle();                                    // vkDeviceWaitIdle

@@ -75,6 +75,7 @@ SYMBOLS = {
     "lum_b200_get_frame_index": (C.c_int, [_P]),
     "lum_b200_download_radiance_field": (None, [_P, _P]),
     "lum_b200_upload_radiance_field": (None, [_P, _P]),
+    "lum_b200_glossy": (None, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "lum_b200_download_block_palette": (None, [_P, C.c_int, C.c_int, _P]),
     "lum_b200_download_world": (None, [_P, _P]),
     "lum_b200_get_material_palette": (None, [_P, _P]),
@@ -236,6 +237,17 @@ class Renderer:
         f = np.ascontiguousarray(field, np.uint32)
         assert f.size == self.cells
         self.lib.lum_b200_upload_radiance_field(self.h, _ptr(f))
+
+    def glossy(self, mat_norm, depth, frame=None):
+        """The glossy pass with the renderer's camera: mat_norm uint8 [h,w,4], depth float32 [h,w] ->
+        (frame float32 [h,w,4], covered uint8 [h,w])."""
+        mn = np.ascontiguousarray(mat_norm, np.uint8)
+        h, w = mn.shape[:2]
+        dp = np.ascontiguousarray(depth, np.float32)
+        fr = np.zeros((h, w, 4), np.float32) if frame is None else np.ascontiguousarray(frame, np.float32)
+        cov = np.zeros((h, w), np.uint8)
+        self.lib.lum_b200_glossy(self.h, w, h, _ptr(mn), _ptr(dp), _ptr(fr), _ptr(cov))
+        return fr, cov
 
     def download_block_palette(self, first, count):
         b = np.empty((count, 16, 16, 16), np.uint8)

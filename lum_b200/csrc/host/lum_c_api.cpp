@@ -135,6 +135,9 @@ long long lum_b200_get_request_count(const LumRenderer instance) { return IR(ins
 int lum_b200_get_frame_index(const LumRenderer instance) { return IR(instance).lumal.iFrame; }
 void lum_b200_download_radiance_field(LumRenderer instance, uint32_t* words) { IR(instance).download_radiance_field(words); }
 void lum_b200_upload_radiance_field(LumRenderer instance, const uint32_t* words) { IR(instance).upload_radiance_field(words); }
+void lum_b200_glossy(LumRenderer instance, int width, int height, const uint8_t* mat_norm, const float* depth, float* frame, uint8_t* covered) {
+    IR(instance).glossy(width, height, mat_norm, depth, frame, covered);
+}
 void lum_b200_download_block_palette(LumRenderer instance, int first, int count, uint8_t* voxels) { IR(instance).download_block_palette(first, count, voxels); }
 void lum_b200_download_world(LumRenderer instance, int16_t* ids) { IR(instance).download_world(ids); }
 void lum_b200_get_material_palette(const LumRenderer instance, float* materials) {

@@ -324,6 +324,16 @@ void LumInternalRenderer::end_frame() {                                  // :208
 // ---- readbacks -------------------------------------------------------------------------------
 void LumInternalRenderer::download_radiance_field(uint32_t* words) { check(lumcu_download_field(stage, words), "lumcu_download_field"); }
 void LumInternalRenderer::upload_radiance_field(const uint32_t* words) { check(lumcu_upload_field(stage, words), "lumcu_upload_field"); }
+void LumInternalRenderer::glossy(int width, int height, const uint8_t* mat_norm, const float* depth, float* frame, uint8_t* covered) {
+    LumcuGlossyView v{};
+    const dvec3 hs = dvec3(camera.horizline.x * camera.viewSize.x / 2.0, camera.horizline.y * camera.viewSize.x / 2.0, camera.horizline.z * camera.viewSize.x / 2.0);
+    const dvec3 vs = dvec3(camera.vertiline.x * camera.viewSize.y / 2.0, camera.vertiline.y * camera.viewSize.y / 2.0, camera.vertiline.z * camera.viewSize.y / 2.0);
+    const double* src[5] = {&camera.cameraPos.x, &camera.cameraDir.x, &hs.x, &vs.x, &lightDir.x};
+    float* dst[5] = {v.campos, v.camdir, v.horizline_scaled, v.vertiline_scaled, v.global_light_dir};
+    for (int k = 0; k < 5; k++) for (int i = 0; i < 3; i++) dst[k][i] = (float)src[k][i];    // vec4(dvec3, 0): double -> float
+    v.frame_size[0] = (float)width; v.frame_size[1] = (float)height;
+    check(lumcu_glossy(stage, &v, width, height, mat_norm, depth, frame, covered), "lumcu_glossy");
+}
 void LumInternalRenderer::download_block_palette(int first, int count, uint8_t* v) { check(lumcu_download_bricks(stage, first, count, v), "lumcu_download_bricks"); }
 void LumInternalRenderer::wait_idle() { if (stage) check(lumcu_wait_idle(stage), "lumcu_wait_idle"); }
 void LumInternalRenderer::download_world(int16_t* ids) { check(lumcu_download_world(stage, ids), "lumcu_download_world"); }

@@ -111,3 +111,40 @@ def test_glossy_device_entry_and_errors(oracle_mod):
     assert st.lib.lumcu_glossy_device(st.ctx, C.byref(v), w, h, 0, dp.data_ptr(), fr.data_ptr(), 0) == -1
     assert st.lib.lumcu_glossy(st.ctx, None, w, h, None, None, None, None) == -1
     st.close()
+
+
+def test_glossy_through_the_lum_api_mirror(oracle_mod, demo):
+    """lum_b200_glossy (include/clum.h): the pass driven from the Lum API mirror, uniform block filled from the
+    renderer's camera the way start_raygen does (internal_render.cpp:1580-1592), after three submitted frames."""
+    O = oracle_mod
+    from lum_b200 import clum
+    mats = demo["materials"].copy()
+    mats[:, 5] *= 0.5                                     # every material glossy
+    r = clum.Renderer((48, 48, 16), 15)
+    r.load_world(demo["world"])
+    for i in range(1, 15):
+        r.load_block(i, demo["bricks"][i])
+    r.set_material_palette(mats)
+    r.upload_block_palette(); r.upload_material_palette()
+    r.set_radiance_controller(False, 1)
+    r.set_camera((60.0, 0.0, 194.0), (0.61, 1.0, -0.8))   # not normalised on purpose: the reference stores it as given
+    for _ in range(3):
+        r.start_frame(); r.prepare_frame(); r.submit_frame()
+    field = r.download_field()
+    w, h = 1920 // 16, 1080 // 16                         # the mirror's camera has the reference's 1920x1080 / 5 view
+    d = np.array([0.61, 1.0, -0.8])
+    plane = np.array([d[0], d[1], 0.0]); plane /= np.linalg.norm(plane)
+    hz = np.cross(plane, [0, 0, 1.0]); hz /= np.linalg.norm(hz)
+    vt = np.cross(d, hz); vt /= np.linalg.norm(vt)
+    view = dict(campos=np.array([60.0, 0.0, 194.0], np.float32), camdir=d.astype(np.float32),
+                horizline_scaled=(hz * (1920 / 5.0) / 2.0).astype(np.float32),
+                vertiline_scaled=(vt * (1080 / 5.0) / 2.0).astype(np.float32),
+                global_light_dir=(np.array([0.5, 0.5, -0.9]) / np.linalg.norm([0.5, 0.5, -0.9])).astype(np.float32),
+                frame_size=np.array([w, h], np.float32))
+    sc = O.Scene(demo["world"], np.concatenate([demo["bricks"], np.zeros((256 - 15, 16, 16, 16), np.uint8)]), mats)
+    mn, dp = O.gbuffer(sc, view, w, h)
+    got, cov = r.glossy(mn, dp)
+    ref = O.glossy(sc, field, view, mn, dp)
+    assert cov.any() and np.array_equal(cov, ref["covered"])
+    assert_bits_equal(got, ref["frame"])
+    r.close()
