@@ -424,9 +424,19 @@ def measure_glossy(torch, device, steps=20, warmup=5):
                                              "d2h_bytes_per_step": int(fr_host.nbytes)}}
 
 
+def host_threads():
+    """All the host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm
+    must not inherit that, so the count is passed to the oracle explicitly (num_threads overrides the variable)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(scene, budget_s, threads=0):
     """The oracle port on the host cores, on a bounded strided sample of the request list."""
     import oracle as O
+    threads = threads or host_threads()
     sc = O.Scene(scene["world"], scene["bricks"], scene["materials"], rays_per_probe=RAYS)
     req = O.build_requests(scene["world"])
     f0 = np.zeros(sc.cells, np.uint32)
@@ -456,10 +466,10 @@ def run_reference(args, rank):
     budget = max(1.0, min(20.0, 150.0 / max(1, nsteps)))
     base, sample, sc, f0 = cpu_baseline(scene, budget)
     for i in range(args.warmup):
-        O.update(sc, f0, sample, i)
+        O.update(sc, f0, sample, i, nthreads=host_threads())
     t0 = time.perf_counter()
     for k in range(args.steps):
-        O.update(sc, f0, sample, args.warmup + k)
+        O.update(sc, f0, sample, args.warmup + k, nthreads=host_threads())
     dt = time.perf_counter() - t0
     value = len(sample) * RAYS * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
