@@ -555,7 +555,9 @@ def run_ours(args, rank, local_rank, world_size):
                 "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
                              "frac": m["frac"], "traffic": load_traffic(args.workload, world_size), "peak_source": peak_src,
                              "kernel": "radiance_update kernel", "kernel_ms": m["kernel_ms"],
-                             "algorithmic_bytes_per_launch": m["alg_bytes"]},
+                             "algorithmic_bytes_per_launch": m["alg_bytes"],
+                             # SURVEY 8d's second figure: what one update must touch at least once
+                             "compulsory_unique_bytes": int(scene["world"].nbytes + scene["bricks"].nbytes + 6144 + 2 * runner.cells * 4)},
                 "clocks": clocks}
         if cb:
             line["cpu_baseline"] = cb
