@@ -387,3 +387,41 @@ def test_round_trip_properties_full_size():
         st.update_slab(1, 1, 0, 32 * r, 32 * r + 32)
         out[32 * r:32 * r + 32] = st.download_field().reshape(64, 256, 256)[32 * r:32 * r + 32]
     assert np.array_equal(out.reshape(-1), f1)
+
+
+def test_full_size_config4_matches_oracle(oracle_mod):
+    """The benchmark's own workload, whole: all 4,191,908 probes x 64 rays of the synthetic 256x256x64 world
+    (BASELINE configs[3]) on a random starting field -- packed field, per-probe pre-blend radiance and the S/H
+    totals of the roofline numerator against the oracle, bit for bit (the oracle needs a few seconds on the box's
+    host cores for the 268 M rays)."""
+    O = oracle_mod
+    scn = scenes.synthetic_scene(256, 256, 64)
+    st = make_stage(scn)
+    sc = oracle_scene(O, scn)
+    n = st.build_requests()
+    req = st.download_requests()
+    assert n == len(req) == 4_191_908
+    rng = np.random.default_rng(4)
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    st.upload_field(f0)
+    st.set_debug(DEBUG_PRE_BLEND)
+    st.update(7)
+    dbg = st.download_debug(n)
+    got = st.download_field()
+    st.set_debug(0)
+    ref = O.update(sc, f0, req, 7)
+    assert dbg["totals"] == ref["totals"]
+    assert np.array_equal(got, ref["field"])
+    # A ray whose direction has an exactly zero component (fib + 0.1*jitter cancels: about one ray in 2^28, i.e. one
+    # or two probes of this update) gets a NaN refined fraction from 0*inf in radiance.comp:257-285, hence NaN
+    # radiance on BOTH sides (the texel then packs as 0, decree 7).  NaN payloads are not part of the contract.
+    nan = np.isnan(ref["pre_blend"])
+    assert np.array_equal(np.isnan(dbg["pre_blend"]), nan) and nan.sum() <= 3 * 4
+    ok = ~nan & (ref["pre_blend"] != 0)
+    assert np.array_equal(dbg["pre_blend"][~nan], ref["pre_blend"][~nan])
+    assert np.array_equal(bits(dbg["pre_blend"])[ok], bits(ref["pre_blend"])[ok])
+    # the non-instrumented production kernel gives the same field
+    st.upload_field(f0)
+    st.update(7)
+    assert np.array_equal(st.download_field(), ref["field"])
+    st.close()
