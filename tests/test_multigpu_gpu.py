@@ -99,5 +99,15 @@ def test_peer_exchange_single_rank_degenerates_to_update(oracle_mod, demo):
     st.upload_field(np.zeros(st.cells, np.uint32))
     for f in range(3):
         st.update(f)
-    assert np.array_equal(got, st.download_field())
+    ref = st.download_field()
+    assert np.array_equal(got, ref)
+    st.upload_field(np.zeros(st.cells, np.uint32))
+    for f in range(3):
+        st.update_shard_exchange(f, 1, 0)            # one shard = the whole dispatch
+    assert np.array_equal(st.download_field(), ref)
     st.peers_close()
+    import lum_b200
+    with pytest.raises(lum_b200.LumcuError):           # no peers any more
+        st.update_shard_exchange(0, 1, 0)
+    with pytest.raises(lum_b200.LumcuError):
+        st.update_shard(0, 1, 0, 2, 2)                 # rank out of range
