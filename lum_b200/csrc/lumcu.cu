@@ -465,7 +465,7 @@ static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, s
         return 0;
     }
     cudaGetLastError();   // cudaPointerGetAttributes on plain pageable memory may leave an error state on old drivers
-    void *h; int slot;
+    void *h = nullptr; int slot = 0;
     if (int rc = st.acquire(bytes, &h, &slot)) return rc;
     memcpy(h, src, bytes);
     CU(cudaMemcpyAsync(dst, h, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -545,7 +545,7 @@ int lumcu_copy_bricks(LumcuCtx *c, const int32_t *src, const int32_t *dst, int32
         CU(cudaMalloc(&c->d_pairs, (size_t)cap * sizeof(int2)));
         c->pairs_cap = cap;
     }
-    void *h; int slot;
+    void *h = nullptr; int slot = 0;
     if (int rc = c->stage_pairs.acquire((size_t)n * sizeof(int2), &h, &slot)) return rc;
     int2 *hp = (int2 *)h;
     for (int i = 0; i < n; i++) { hp[i].x = src[i]; hp[i].y = dst[i]; if (dst[i] == 0) c->brick0_empty = false; }
