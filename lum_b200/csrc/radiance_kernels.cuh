@@ -103,16 +103,16 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
 // One CTA owns a batch of NR = RPT*THREADS rays (NR/R probes) staged in shared memory:
 //   A  ray setup, one ray per thread per round, fully convergent.
 //   B  coarse march with lane-level dynamic refill from the CTA's ray pool: a lane whose ray
-//      ended immediately takes the next ray, so warps stay ~90 % full although ray lengths vary
-//      8x.  When the pool is empty and a warp is down to < PARK live lanes it parks its unfinished
+//      ended immediately takes the next ray, so warps stay ~80 % full although ray lengths vary
+//      1..67 samples.  When the pool is empty and a warp is down to < PARK live lanes it parks its unfinished
 //      rays (their t goes back to the slot) and leaves.
 //   B' the parked stragglers (~10 % of the rays, the long ones) are compacted into a few "tail"
 //      warps, which march them in further passes among themselves (named barrier), while
 //   C  every other warp already runs refinement + shading on the finished rays, 32 slots per
 //      claim, convergent again.  The tail warps join C when they are done and finally shade the
 //      stragglers.  So nobody idles behind the longest ray of the batch.
-//   D  the workgroup reduction of radiance.comp:386-413 (xor butterfly per 32-ray subgroup) and
-//      store_probe; one warp per probe.
+//   D  the workgroup reduction of radiance.comp:386-413 (xor butterfly per 32-ray subgroup, the
+//      subgroups spread over the warps) and store_probe, one thread per probe.
 // The result does not depend on the schedule: each ray's sample sequence is a function of its
 // own (o, d, t) only, and the reduction tree is fixed.
 struct PoolRay { f3 o, d, inv; float t; int ns; i3 cm; };
