@@ -425,3 +425,36 @@ def test_full_size_config4_matches_oracle(oracle_mod):
     st.update(7)
     assert np.array_equal(st.download_field(), ref["field"])
     st.close()
+
+
+@pytest.mark.parametrize("case", range(32))
+def test_random_small_worlds(oracle_mod, case):
+    """Fuzz: odd world sizes (down to a single block), sparse to solid bricks, palettes of 1..40 bricks, requests
+    that include duplicates' neighbours, out-of-world probes and a ragged workgroup count, random fields and seeds --
+    every kernel variant against the oracle, bit for bit."""
+    O = oracle_mod
+    rng = np.random.default_rng(1000 + case)
+    wx, wy, wz = (int(v) for v in rng.integers(1, [9, 8, 5]))
+    P = int(rng.integers(2, 41))
+    bricks = (rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))
+    bricks = bricks.astype(np.uint8)
+    if case % 3:
+        bricks[0] = 0                                   # two thirds of the cases keep brick 0 empty (fast march)
+    world = (rng.random((wz, wy, wx)) < rng.choice([0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))
+    world = world.astype(np.int16)
+    if case % 8 == 7:
+        world.reshape(-1)[0] = P + 3                    # an id outside the palette (general march via the device flag)
+    mats = rng.random((256, 6)).astype(np.float32)
+    mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
+    scn = dict(world=world, bricks=bricks, materials=mats)
+    st = make_stage(scn)
+    sc = oracle_scene(O, scn)
+    inside = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+    outside = np.array([(-1, 0, 0, 0), (wx, 0, 0, 0), (0, -2, wz, 0), (wx + 3, wy + 1, -1, 0)], np.int16)
+    req = np.concatenate([inside, outside])
+    req = req[rng.permutation(len(req))][: max(1, int(rng.integers(1, len(req) + 1)))]
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    size = int(rng.integers(1, 4))
+    size = min(size, len(req))
+    assert_update_equal(st, O, sc, f0, req, int(rng.integers(-2 ** 31, 2 ** 31)), size=size, shift=int(rng.integers(0, size)))
+    st.close()
