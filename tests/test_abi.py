@@ -74,3 +74,18 @@ def test_product_does_not_import_oracle():
                     if re.search(r"\b(import oracle|from oracle|lum_oracle|liblum_oracle)", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_api_mirror_symbols_exported():
+    """liblum.so exports every lum_* / lum_b200_* function include/clum.h declares, and the ctypes binding
+    (lum_b200/clum.py) covers exactly that surface."""
+    from lum_b200 import clum
+    lbuild.build_all()
+    src = open(os.path.join(ROOT, "include", "clum.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lum_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) >= 37 and "lum_b200_glossy" in names
+    raw = ctypes.CDLL(clum.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/clum.h but not exported"
+    assert sorted(clum.SYMBOLS) == names
