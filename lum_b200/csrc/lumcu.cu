@@ -87,6 +87,7 @@ struct LumcuCtx {
     int16_t *d_world = nullptr;
     uint8_t *d_bricks = nullptr;
     float *d_materials = nullptr;
+    float4 *d_mat4 = nullptr;              // {r,g,b,emmit} per id, repacked at upload (the shading phase's one load)
     uint32_t *d_field = nullptr;
     uint32_t *d_field_tmp = nullptr;       // shift scratch (lazy)
     short4 *d_requests = nullptr;
@@ -263,7 +264,7 @@ int ensure_validated(LumcuCtx *c) {
 }
 
 SceneView scene_view(LumcuCtx *c) {
-    return SceneView{c->d_world, c->d_bricks, c->d_materials, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
+    return SceneView{c->d_world, c->d_bricks, c->d_materials, c->d_mat4, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
                      c->brick0_empty ? 1 : 0, c->d_scene_flags};
 }
 
@@ -397,6 +398,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaMalloc(&c->d_scene_flags, sizeof(uint32_t)));
     CUB(cudaMalloc(&c->d_bricks, (size_t)d->palette_capacity * 4096));
     CUB(cudaMalloc(&c->d_materials, 256 * 6 * sizeof(float)));
+    CUB(cudaMalloc(&c->d_mat4, 256 * sizeof(float4)));
     CUB(cudaMalloc(&c->d_field, (size_t)c->cells * sizeof(uint32_t)));
     CUB(cudaMalloc(&c->d_requests, (size_t)c->max_requests * sizeof(short4)));
     CUB(cudaMalloc(&c->d_staged, (size_t)c->max_requests * sizeof(uint32_t)));
@@ -404,6 +406,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaMemsetAsync(c->d_world, 0, (size_t)c->cells * sizeof(int16_t), c->stream));
     CUB(cudaMemsetAsync(c->d_bricks, 0, (size_t)d->palette_capacity * 4096, c->stream));
     CUB(cudaMemsetAsync(c->d_materials, 0, 256 * 6 * sizeof(float), c->stream));
+    CUB(cudaMemsetAsync(c->d_mat4, 0, 256 * sizeof(float4), c->stream));
     CUB(cudaMemsetAsync(c->d_field, 0, (size_t)c->cells * sizeof(uint32_t), c->stream));   // initial field = zero words
     if (const char *e = getenv("LUMCU_POOL_THREADS")) c->pool_threads = atoi(e) == 256 ? 256 : 128;
     if (const char *e = getenv("LUMCU_CARVEOUT")) c->carveout = atoi(e);
@@ -427,7 +430,7 @@ int lumcu_destroy(LumcuCtx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_scene_flags);
     cudaFree(c->d_g_matnorm); cudaFree(c->d_g_depth); cudaFree(c->d_g_frame); cudaFree(c->d_g_cov);
-    cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_field);
+    cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_mat4); cudaFree(c->d_field);
     cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
     cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
     lumcu_peers_close(c);
@@ -502,6 +505,12 @@ int lumcu_upload_materials(LumcuCtx *c, const float *m) {
     if (int rc = use(c)) return rc;
     if (!m) return fail(LUMCU_E_ARG, "null materials");
     if (int rc = staged_upload(c, c->stage_misc, c->d_materials, m, 256 * 6 * sizeof(float))) return rc;
+    float packed[256 * 4];     // device mirror for the tracer: the floats a hit uses (r, g, b, emmit) side by side
+    for (int i = 0; i < 256; i++) {
+        packed[4 * i + 0] = m[6 * i + 0]; packed[4 * i + 1] = m[6 * i + 1];
+        packed[4 * i + 2] = m[6 * i + 2]; packed[4 * i + 3] = m[6 * i + 4];
+    }
+    if (int rc = staged_upload(c, c->stage_misc, c->d_mat4, packed, sizeof packed)) return rc;
     c->have_materials = true;
     return 0;
 }

@@ -17,6 +17,7 @@ struct SceneView {
     const int16_t *__restrict__ world;      // [z][y][x] block ids
     const uint8_t *__restrict__ bricks;     // [id][x][y][z] material ids
     const float *__restrict__ materials;    // [256][6]
+    const float4 *__restrict__ mat4;        // [256] {r, g, b, emmit}: the four floats GetMat's callers use, one 16-byte load
     const uint32_t *__restrict__ field;     // [z][y][x] packed A2B10G10R10 (read side)
     int wx, wy, wz;
     int capacity;                           // bricks addressable
@@ -321,8 +322,8 @@ __device__ __forceinline__ f3 finish_ray(const SceneView &s, const f3 &o, const 
         float tf;
         int vid;
         refine_hit<true, VALID>(s, o, d, inv, t, n, tf, vid, refine_samples);
-        const float *m = s.materials + 6 * (vid & 255);
-        float mr = __ldg(m), mg = __ldg(m + 1), mb = __ldg(m + 2), me = __ldg(m + 4);
+        const float4 m = __ldg(s.mat4 + (vid & 255));     // GetMat (radiance.comp:145-157): r, g, b, emmit
+        const float mr = m.x, mg = m.y, mb = m.z, me = m.w;
         f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
         f3 bp = {(x.x + n.x * 16.0f) / 16.0f, (x.y + n.y * 16.0f) / 16.0f, (x.z + n.z * 16.0f) / 16.0f};
         f3 g = gather_field(s, bp);

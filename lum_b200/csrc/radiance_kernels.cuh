@@ -542,8 +542,8 @@ __global__ void __launch_bounds__(128) glossy_kernel(SceneView s, GlossyArgs a) 
         int vid, nr;
         if (fast) refine_hit<false, true>(s, o, d, inv, t, n2, tf, vid, nr);
         else refine_hit<false, false>(s, o, d, inv, t, n2, tf, vid, nr);
-        const float *m2 = s.materials + 6 * (vid & 255);
-        const float r2 = __ldg(m2), g2 = __ldg(m2 + 1), b2 = __ldg(m2 + 2), e2 = __ldg(m2 + 4);
+        const float4 m2 = __ldg(s.mat4 + (vid & 255));
+        const float r2 = m2.x, g2 = m2.y, b2 = m2.z, e2 = m2.w;
         const f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
         const f3 gg = gather_field(s, {(x.x + n2.x * 16.0f) / 16.0f, (x.y + n2.y * 16.0f) / 16.0f, (x.z + n2.z * 16.0f) / 16.0f});
         refl = {refl.x * r2, refl.y * g2, refl.z * b2};
