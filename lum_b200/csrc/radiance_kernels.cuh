@@ -504,8 +504,8 @@ __global__ void __launch_bounds__(128) glossy_kernel(SceneView s, GlossyArgs a) 
     if (px >= a.width || py >= a.height) return;
     const size_t pi = (size_t)py * a.width + px;
     const uchar4 mn = a.mat_norm[pi];
-    const float *m = s.materials + 6 * (int)mn.x;                       // GetMat(load_mat(pix)) :443, :85-96
-    const float mr = __ldg(m), mg = __ldg(m + 1), mb = __ldg(m + 2), me = __ldg(m + 4), rough = __ldg(m + 5);
+    const float4 m = __ldg(s.mat4 + (int)mn.x);                         // GetMat(load_mat(pix)) :443, :85-96
+    const float mr = m.x, mg = m.y, mb = m.z, me = m.w, rough = __ldg(s.materials + 6 * (int)mn.x + 5);
     const bool cov = !(rough > 0.5f);
     if (a.covered) a.covered[pi] = cov ? 1 : 0;
     if (!cov) return;
