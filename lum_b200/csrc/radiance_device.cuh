@@ -231,6 +231,68 @@ __device__ __forceinline__ bool march_step_fast(const SceneView &s, const uint3 
     return hit || out || !(t < 128.0f);
 }
 
+// ---- two iterations at once, the second one's block-id fetch issued early (the pooled kernel's loop body;
+// -DLUMCU_NO_SPEC2 builds the two separate steps instead) ---------------------------------------------------
+// A step is two dependent fetches (block id, then voxel), so two steps are four fetch latencies in a row.  But the
+// position of step B depends on step A's block id only (the empty-cell skip), not on A's voxel: B's block id can be
+// requested while A's voxel is still in flight -- id_A -> (voxel_A | id_B) -> voxel_B, three latencies instead of
+// four.  The early fetch is speculative only in that a ray ending at A does not need it; its address is in-world by
+// B's own bounds test, and a lane that is done at A would idle through B under lock-step anyway.  Every value a
+// continuing ray sees is computed exactly as by two calls of march_step_fast.  steps = iterations the ray took.
+__device__ __forceinline__ bool march_two_steps_fast(const SceneView &s, const uint3 &wsbits, const f3 &o, const f3 &d,
+                                                     const f3 &inv, const i3 &cm, float &t, float &t_pre, bool &hit,
+                                                     int &steps) {
+    // step A up to its block id
+    const float tA = t + 0.5f;
+    const float pxA = o.x + d.x * tA, pyA = o.y + d.y * tA, pzA = o.z + d.z * tA;
+    const bool outA = __float_as_uint(pxA) >= wsbits.x || __float_as_uint(pyA) >= wsbits.y || __float_as_uint(pzA) >= wsbits.z;
+    const int ixA = f2i(pxA), iyA = f2i(pyA), izA = f2i(pzA);
+    const int bxA = ixA >> 4, byA = iyA >> 4, bzA = izA >> 4;
+    int idA = 0;
+    if (!outA) idA = __ldg(s.world + (bxA + s.wx * (byA + s.wy * bzA)));
+    const int VA = mad16(mad16(ixA, iyA), izA), BA = mad16(mad16(bxA, byA), bzA);
+    int voxA = 0;
+    if (idA != 0) voxA = __ldg(s.bricks + (uint32_t)(idA * 4096 + msub16(BA, VA)));
+    const float cxA = __int_as_float(mad16(bxA, cm.x)) - 8388608.0f;
+    const float cyA = __int_as_float(mad16(byA, cm.y)) - 8388608.0f;
+    const float czA = __int_as_float(mad16(bzA, cm.z)) - 8388608.0f;
+    const float exA = cxA * inv.x + (-pxA * inv.x);
+    const float eyA = cyA * inv.y + (-pyA * inv.y);
+    const float ezA = czA * inv.z + (-pzA * inv.z);
+    const float tnA = tA + gmax(gmin(exA, gmin(eyA, ezA)), 0.01f);
+    const float tA2 = (idA == 0) ? tnA : tA;
+    // step B up to its block id: needs tA2 (A's block id), not A's voxel
+    const float tB = tA2 + 0.5f;
+    const float pxB = o.x + d.x * tB, pyB = o.y + d.y * tB, pzB = o.z + d.z * tB;
+    const bool outB = __float_as_uint(pxB) >= wsbits.x || __float_as_uint(pyB) >= wsbits.y || __float_as_uint(pzB) >= wsbits.z;
+    const int ixB = f2i(pxB), iyB = f2i(pyB), izB = f2i(pzB);
+    const int bxB = ixB >> 4, byB = iyB >> 4, bzB = izB >> 4;
+    int idB = 0;
+    if (!outB) idB = __ldg(s.world + (bxB + s.wx * (byB + s.wy * bzB)));
+    // A ends here
+    const bool hitA = voxA != 0;
+    const bool doneA = hitA || outA || !(tA2 < 128.0f);
+    // rest of step B (its voxel is only fetched for a ray that got this far)
+    const int VB = mad16(mad16(ixB, iyB), izB), BB = mad16(mad16(bxB, byB), bzB);
+    int voxB = 0;
+    if (idB != 0 && !doneA) voxB = __ldg(s.bricks + (uint32_t)(idB * 4096 + msub16(BB, VB)));
+    const float cxB = __int_as_float(mad16(bxB, cm.x)) - 8388608.0f;
+    const float cyB = __int_as_float(mad16(byB, cm.y)) - 8388608.0f;
+    const float czB = __int_as_float(mad16(bzB, cm.z)) - 8388608.0f;
+    const float exB = cxB * inv.x + (-pxB * inv.x);
+    const float eyB = cyB * inv.y + (-pyB * inv.y);
+    const float ezB = czB * inv.z + (-pzB * inv.z);
+    const float tnB = tB + gmax(gmin(exB, gmin(eyB, ezB)), 0.01f);
+    const float tB2 = (idB == 0) ? tnB : tB;
+    const bool hitB = voxB != 0;
+    const bool doneB = hitB || outB || !(tB2 < 128.0f);
+    t = doneA ? tA2 : tB2;
+    t_pre = doneA ? tA : tB;
+    hit = doneA ? hitA : hitB;
+    steps = doneA ? 1 : 2;
+    return doneA || doneB;
+}
+
 // A ray that ended without an in-world hit stored -t_pre.  If its last position was outside the world the
 // reference still sampled there before the bounds test (radiance.comp:212-237): take that one sample with
 // the general get_voxel.  Returns true if it hit after all; the fraction is then t_pre itself (brick 0 is

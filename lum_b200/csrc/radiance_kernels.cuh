@@ -205,6 +205,22 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
 #ifndef LUMCU_STEPS
 #define LUMCU_STEPS 2
 #endif
+#if !defined(LUMCU_NO_SPEC2) && LUMCU_STEPS == 2
+        if constexpr (FAST) {
+            if (cur >= 0) {
+                bool hit;
+                float t_end;
+                int steps;
+                const bool done = march_two_steps_fast(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit, steps);
+                q.ns += steps;
+                if (done) {
+                    sm.a[cur].w = hit ? q.t : -t_end;
+                    if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
+                    cur = -1;
+                }
+            }
+        } else
+#endif
 #pragma unroll
         for (int rep = 0; rep < LUMCU_STEPS; rep++)
         if (cur >= 0) {
