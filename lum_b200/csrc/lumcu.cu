@@ -774,7 +774,7 @@ int lumcu_ipc_export(LumcuCtx *c, uint8_t *handle) {
 
 int lumcu_peers_close(LumcuCtx *c) {
     if (!c) return 0;
-    if (c->have_peers) {
+    if (c->have_peers || c->n_peer_opened > 0) {   // also after a lumcu_peers_open that failed half-way
         cudaSetDevice(c->desc.device);
         if (c->stream) cudaStreamSynchronize(c->stream);
         for (int i = 0; i < c->n_peer_opened; i++) cudaIpcCloseMemHandle(c->peer_opened[i]);
