@@ -176,15 +176,25 @@ __device__ __forceinline__ int march_step(const SceneView &s, const MarchConsts 
 
 // 16*b + c as ONE multiply-add on the FMA pipe (left to itself the compiler re-derives 16*b as `i & ~15` on the
 // ALU pipe, the one this loop is short of, and adds separately).
+// (The #else branches exist for tests/device_host, which compiles this header with g++ to run the device
+// arithmetic against the oracle where there is no GPU; nvcc's device pass never sees them.)
 __device__ __forceinline__ int mad16(int b, int c) {
+#ifdef __CUDA_ARCH__
     int r;
     asm("mad.lo.s32 %0, %1, 16, %2;" : "=r"(r) : "r"(b), "r"(c));
     return r;
+#else
+    return (int)((unsigned)b * 16u + (unsigned)c);
+#endif
 }
 __device__ __forceinline__ int msub16(int b, int c) {     // c - 16*b
+#ifdef __CUDA_ARCH__
     int r;
     asm("mad.lo.s32 %0, %1, -16, %2;" : "=r"(r) : "r"(b), "r"(c));
     return r;
+#else
+    return (int)((unsigned)c - (unsigned)b * 16u);
+#endif
 }
 
 // ---- the same iteration for the validated device mirror -----------------------------------

@@ -1,0 +1,138 @@
+"""The CUDA kernels' per-thread arithmetic, compiled for the host, against the oracle -- no GPU needed.
+
+lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the three march variants, pending-sample resolution,
+refinement, material fetch, field gather, shading, unorm10 pack/unpack) is compiled with g++ through
+tests/device_host/cuda_host_shim.hpp and run one "thread" after another by tests/device_host/device_on_host.cpp,
+which restates only the workgroup reduction and the blend around it.  This is test infrastructure: it checks the
+device SOURCE where there is no device (a change to the march that breaks parity shows up here before any GPU
+time is spent); the `-m gpu` tests remain the parity tests of the kernels proper.  Bar: bit-exact, like on the GPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "device_host", "device_on_host.cpp")
+DEPS = [SRC, os.path.join(HERE, "device_host", "cuda_host_shim.hpp"),
+        os.path.join(HERE, "..", "lum_b200", "csrc", "radiance_device.cuh")]
+OUT = os.path.join(HERE, "_build", "libdevice_on_host.so")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+MODES = {"general": 0, "fast": 1, "fused": 2}
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+        # -ffp-contract=off = nvcc -fmad=false: one rounding per written operation (DESIGN.md decree 4)
+        r = subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                            "-Wno-unknown-pragmas", "-I", CUDA_INC, "-o", OUT, SRC], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    lib = C.CDLL(OUT)
+    lib.device_on_host_update.restype = C.c_int
+    return lib
+
+
+def run(lib, O, scn, f0, req, seed, mode, rays=64, size=1, shift=0, reactiveness=0.01):
+    world = np.ascontiguousarray(scn["world"], np.int16)
+    bricks = np.ascontiguousarray(scn["bricks"], np.uint8)
+    mats = np.ascontiguousarray(scn["materials"], np.float32)
+    wz, wy, wx = world.shape
+    req = np.ascontiguousarray(req, np.int16).reshape(-1, 4)
+    nwg = len(req) // size
+    f0 = np.ascontiguousarray(f0, np.uint32).reshape(-1)
+    f1 = np.empty_like(f0)
+    pre = np.zeros((nwg, 3), np.float32)
+    rs = np.zeros(nwg * rays, np.uint32)
+    rh = np.zeros(nwg * rays, np.uint8)
+    table = np.ascontiguousarray(O.direction_table(rays), np.float32)
+    sun = np.ascontiguousarray(O.sun_dir(), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.device_on_host_update(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]),
+                                   C.c_int(int(not bricks[0].any())), C.c_int(rays), C.c_float(reactiveness),
+                                   p(world), p(bricks), p(mats), p(f0), p(f1), p(req), C.c_longlong(len(req)),
+                                   C.c_int(seed), C.c_int(size), C.c_int(shift), p(table), p(sun), C.c_int(mode),
+                                   p(pre), p(rs), p(rh))
+    assert rc == 0
+    return dict(field=f1, pre_blend=pre, ray_samples=rs, ray_hits=rh)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_same(got, ref):
+    assert np.array_equal(got["ray_samples"], ref["ray_samples"])
+    assert np.array_equal(got["ray_hits"], ref["ray_hits"])
+    nan = np.isnan(ref["pre_blend"])
+    assert np.array_equal(np.isnan(got["pre_blend"]), nan)
+    assert np.array_equal(got["pre_blend"][~nan], ref["pre_blend"][~nan])          # value-equal (+0 == -0)
+    nz = ~nan & (ref["pre_blend"] != 0)
+    assert np.array_equal(bits(got["pre_blend"])[nz], bits(ref["pre_blend"])[nz])    # and bit-equal where non-zero
+    assert np.array_equal(got["field"], ref["field"])
+
+
+def scene_of(O, scn, rays=64, reactiveness=0.01):
+    return O.Scene(scn["world"], scn["bricks"], scn["materials"], rays_per_probe=rays, reactiveness=reactiveness)
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_demo_world_full_recompute(host_lib, oracle_mod, demo, mode):
+    """BASELINE configs[1]: all 2,689 probes x 64 rays of the demo world on a random field, each march variant."""
+    O = oracle_mod
+    sc = scene_of(O, demo)
+    req = O.build_requests(demo["world"])
+    assert len(req) == 2689
+    f0 = np.random.default_rng(3).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 5, want_rays=True)
+    assert_same(run(host_lib, O, demo, f0, req, 5, MODES[mode]), ref)
+
+
+@pytest.mark.parametrize("rays", [16, 32, 64, 128, 256])
+def test_synthetic_all_ray_counts(host_lib, oracle_mod, small_synth, rays):
+    """Dense random world (the C4 generator at 24x20x12), every supported rays-per-probe, fast and fused march."""
+    O = oracle_mod
+    sc = scene_of(O, small_synth, rays=rays)
+    req = O.build_requests(small_synth["world"])[::7]
+    f0 = np.random.default_rng(rays).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 11, want_rays=True)
+    for mode in ("fast", "fused"):
+        assert_same(run(host_lib, O, small_synth, f0, req, 11, MODES[mode], rays=rays), ref)
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_random_small_worlds(host_lib, oracle_mod, case):
+    """The fuzz of tests/test_parity_gpu.py::test_random_small_worlds on the host build: odd world sizes, sparse to
+    solid bricks, out-of-world probes, ragged workgroup counts, random fields and seeds.  Scenes the device would
+    send down the general march (brick 0 loaded) run mode 0 only."""
+    O = oracle_mod
+    rng = np.random.default_rng(1000 + case)
+    wx, wy, wz = (int(v) for v in rng.integers(1, [9, 8, 5]))
+    P = int(rng.integers(2, 41))
+    bricks = (rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))
+    bricks = bricks.astype(np.uint8)
+    if case % 3:
+        bricks[0] = 0
+    world = ((rng.random((wz, wy, wx)) < rng.choice([0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
+    mats = rng.random((256, 6)).astype(np.float32)
+    mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
+    scn = dict(world=world, bricks=bricks, materials=mats)
+    sc = scene_of(O, scn)
+    inside = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+    outside = np.array([(-1, 0, 0, 0), (wx, 0, 0, 0), (0, -2, wz, 0), (wx + 3, wy + 1, -1, 0)], np.int16)
+    req = np.concatenate([inside, outside])
+    req = req[rng.permutation(len(req))][: max(1, int(rng.integers(1, len(req) + 1)))]
+    f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    size = min(int(rng.integers(1, 4)), len(req))
+    shift = int(rng.integers(0, size))
+    seed = int(rng.integers(-2 ** 31, 2 ** 31))
+    ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=True)
+    modes = ("general", "fast", "fused") if not bricks[0].any() else ("general",)
+    for mode in modes:
+        assert_same(run(host_lib, O, scn, f0, req, seed, MODES[mode], size=size, shift=shift), ref)
