@@ -366,6 +366,47 @@ __device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, cons
     f3 tDelta = {fabsf(inv.x), fabsf(inv.y), fabsf(inv.z)};   // 1/|d| == |1/d| exactly
     int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#ifdef LUMCU_REFINE_AHEAD     // opt-in until measured
+    if constexpr (VALID) {
+        // The voxels the DDA visits do not depend on the fetched data, so the block id of voxel k+1 is requested
+        // while voxel k is still in flight: one fetch latency per step instead of two.  id < 0 marks a voxel outside
+        // the world, which takes the general get_voxel.  Same fetch results, same step order as the loop below.
+        const unsigned ex = (unsigned)(s.wx << 4), ey = (unsigned)(s.wy << 4), ez = (unsigned)(s.wz << 4);
+        auto block_id = [&](int x, int y, int z) -> int {
+            int id = -1;
+            if ((unsigned)x < ex && (unsigned)y < ey && (unsigned)z < ez)
+                id = __ldg(s.world + ((x >> 4) + s.wx * ((y >> 4) + s.wy * (z >> 4))));
+            return id;
+        };
+        auto voxel_of = [&](int id, int x, int y, int z) -> int {
+            if (id < 0) { int b; return get_voxel(s, x, y, z, b); }
+            int v = 0;
+            if (id != 0) v = __ldg(s.bricks + (uint32_t)(id * 4096 + (((x & 15) << 8) | ((y & 15) << 4) | (z & 15))));
+            return v;
+        };
+        int id = block_id(vx, vy, vz);
+        int ns = 0, it = 0;
+        for (;;) {
+            const int pending = voxel_of(id, vx, vy, vz);         // voxel k: in flight
+            const float nax = ((tMax.x <= tMax.y) && (tMax.x <= tMax.z)) ? 1.0f : 0.0f;
+            const float nay = ((tMax.x >= tMax.y) && (tMax.y <= tMax.z)) ? 1.0f : 0.0f;
+            const float naz = ((tMax.z <= tMax.x) && (tMax.z <= tMax.y)) ? 1.0f : 0.0f;
+            const int nx = vx + stx * (int)nax, ny = vy + sty * (int)nay, nz = vz + stz * (int)naz;
+            const int nid = block_id(nx, ny, nz);                 // block id of voxel k+1: in flight with it
+            vid = pending;
+            ns++;
+            if (!((it++ <= 4) && (vid == 0))) break;
+            ax = nax; ay = nay; az = naz;
+            vx = nx; vy = ny; vz = nz;
+            tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
+            id = nid;
+        }
+        refine_samples = ns;
+        n = {-((float)stx * ax), -((float)sty * ay), -((float)stz * az)};
+        tf = (tMax.x - tDelta.x) * ax + (tMax.y - tDelta.y) * ay + (tMax.z - tDelta.z) * az;
+        return;
+    }
+#endif
     vid = get_voxel_v<VALID>(s, vx, vy, vz);
     int ns = 1;
     int it = 0;
@@ -425,7 +466,12 @@ __device__ __forceinline__ bool march_ray(const SceneView &s, const MarchConsts 
         const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
         float t_pre;
         bool hit;
+#ifdef LUMCU_SPEC2_WG     // opt-in until measured: the fused two-step march for the one-thread-per-ray kernels too
+        int steps;
+        while (!march_two_steps_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit, steps)) {}
+#else
         while (!march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit)) {}
+#endif
         if (hit) return true;
         // Ended without an in-world hit.  Unlike the probe rays, whose origins are built by setup_ray, these
         // origins come from the caller: a position of -0.0 or NaN is "out" for the bit test but not for
@@ -464,7 +510,12 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
         const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
         float t_pre;
         bool done;
+#ifdef LUMCU_SPEC2_WG
+        int steps;
+        do { done = march_two_steps_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit, steps); samples += steps; } while (!done);
+#else
         do { done = march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit); samples++; } while (!done);
+#endif
         if (!hit && resolve_pending(s, mc, o, d, t_pre)) { hit = true; t = t_pre; }
     } else {
         int st;

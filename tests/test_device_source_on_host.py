@@ -24,19 +24,32 @@ CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 MODES = {"general": 0, "fast": 1, "fused": 2}
 
 
-@pytest.fixture(scope="module")
-def host_lib():
+def build_host_lib(out, defines=()):
     if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
         pytest.skip("CUDA headers not found")
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS):
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS + [__file__]):
         # -ffp-contract=off = nvcc -fmad=false: one rounding per written operation (DESIGN.md decree 4)
         r = subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                            "-Wno-unknown-pragmas", "-I", CUDA_INC, "-o", OUT, SRC], capture_output=True, text=True)
+                            "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines], "-I", CUDA_INC, "-o", out, SRC],
+                           capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
-    lib = C.CDLL(OUT)
+    lib = C.CDLL(out)
     lib.device_on_host_update.restype = C.c_int
     return lib
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    return build_host_lib(OUT)
+
+
+@pytest.fixture(scope="module")
+def host_lib_optin():
+    """The compile-time variants that are built but not yet the default: the fused two-step
+    march in the one-thread-per-ray kernels and the one-ahead refinement.  Kept bit-exact here until a GPU round
+    measures them."""
+    return build_host_lib(OUT.replace(".so", "_optin.so"), ("LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD"))
 
 
 def run(lib, O, scn, f0, req, seed, mode, rays=64, size=1, shift=0, reactiveness=0.01):
@@ -136,3 +149,15 @@ def test_random_small_worlds(host_lib, oracle_mod, case):
     modes = ("general", "fast", "fused") if not bricks[0].any() else ("general",)
     for mode in modes:
         assert_same(run(host_lib, O, scn, f0, req, seed, MODES[mode], size=size, shift=shift), ref)
+
+
+@pytest.mark.parametrize("mode", ["fast", "fused"])
+def test_optin_variants_stay_bit_exact(host_lib_optin, oracle_mod, demo, small_synth, mode):
+    """-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD (off by default): demo world and the dense synthetic world."""
+    O = oracle_mod
+    for scn, stride, rays in ((demo, 1, 64), (small_synth, 5, 64), (small_synth, 11, 16)):
+        sc = scene_of(O, scn, rays=rays)
+        req = O.build_requests(scn["world"])[::stride]
+        f0 = np.random.default_rng(rays + stride).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+        ref = O.update(sc, f0, req, 9, want_rays=True)
+        assert_same(run(host_lib_optin, O, scn, f0, req, 9, MODES[mode], rays=rays), ref)
