@@ -303,6 +303,78 @@ __device__ __forceinline__ bool march_two_steps_fast(const SceneView &s, const u
     return doneA || doneB;
 }
 
+// ---- the same pair of steps with the NEXT pair's first block id already requested (opt-in: -DLUMCU_ROLL) ------
+// Roll carries the front half of the step that follows: the sample position at t + 0.5 and its block id (0 when the
+// position is outside the world).  In steady state a pair of steps then waits for two fetch latencies
+// (voxel_A | id_B, voxel_B | id_C) instead of three.  roll_prime() fills it for a ray that was just (re)loaded.
+struct Roll { float px, py, pz; int id; };
+
+__device__ __forceinline__ void roll_prime(const SceneView &s, const uint3 &wsbits, const f3 &o, const f3 &d, float t, Roll &r) {
+    const float tA = t + 0.5f;
+    r.px = o.x + d.x * tA; r.py = o.y + d.y * tA; r.pz = o.z + d.z * tA;
+    const bool out = __float_as_uint(r.px) >= wsbits.x || __float_as_uint(r.py) >= wsbits.y || __float_as_uint(r.pz) >= wsbits.z;
+    r.id = 0;
+    if (!out) r.id = __ldg(s.world + ((f2i(r.px) >> 4) + s.wx * ((f2i(r.py) >> 4) + s.wy * (f2i(r.pz) >> 4))));
+}
+
+__device__ __forceinline__ bool march_two_steps_rolling(const SceneView &s, const uint3 &wsbits, const f3 &o, const f3 &d,
+                                                        const f3 &inv, const i3 &cm, float &t, float &t_pre, bool &hit,
+                                                        int &steps, Roll &r) {
+    // step A: position and block id were produced by the previous pair (or by roll_prime)
+    const float tA = t + 0.5f;
+    const float pxA = r.px, pyA = r.py, pzA = r.pz;
+    const bool outA = __float_as_uint(pxA) >= wsbits.x || __float_as_uint(pyA) >= wsbits.y || __float_as_uint(pzA) >= wsbits.z;
+    const int ixA = f2i(pxA), iyA = f2i(pyA), izA = f2i(pzA);
+    const int bxA = ixA >> 4, byA = iyA >> 4, bzA = izA >> 4;
+    const int idA = r.id;
+    const int VA = mad16(mad16(ixA, iyA), izA), BA = mad16(mad16(bxA, byA), bzA);
+    int voxA = 0;
+    if (idA != 0) voxA = __ldg(s.bricks + (uint32_t)(idA * 4096 + msub16(BA, VA)));
+    const float cxA = __int_as_float(mad16(bxA, cm.x)) - 8388608.0f;
+    const float cyA = __int_as_float(mad16(byA, cm.y)) - 8388608.0f;
+    const float czA = __int_as_float(mad16(bzA, cm.z)) - 8388608.0f;
+    const float exA = cxA * inv.x + (-pxA * inv.x);
+    const float eyA = cyA * inv.y + (-pyA * inv.y);
+    const float ezA = czA * inv.z + (-pzA * inv.z);
+    const float tnA = tA + gmax(gmin(exA, gmin(eyA, ezA)), 0.01f);
+    const float tA2 = (idA == 0) ? tnA : tA;
+    // step B up to its block id
+    const float tB = tA2 + 0.5f;
+    const float pxB = o.x + d.x * tB, pyB = o.y + d.y * tB, pzB = o.z + d.z * tB;
+    const bool outB = __float_as_uint(pxB) >= wsbits.x || __float_as_uint(pyB) >= wsbits.y || __float_as_uint(pzB) >= wsbits.z;
+    const int ixB = f2i(pxB), iyB = f2i(pyB), izB = f2i(pzB);
+    const int bxB = ixB >> 4, byB = iyB >> 4, bzB = izB >> 4;
+    int idB = 0;
+    if (!outB) idB = __ldg(s.world + (bxB + s.wx * (byB + s.wy * bzB)));
+    const bool hitA = voxA != 0;
+    const bool doneA = hitA || outA || !(tA2 < 128.0f);
+    const int VB = mad16(mad16(ixB, iyB), izB), BB = mad16(mad16(bxB, byB), bzB);
+    int voxB = 0;
+    if (idB != 0 && !doneA) voxB = __ldg(s.bricks + (uint32_t)(idB * 4096 + msub16(BB, VB)));
+    const float cxB = __int_as_float(mad16(bxB, cm.x)) - 8388608.0f;
+    const float cyB = __int_as_float(mad16(byB, cm.y)) - 8388608.0f;
+    const float czB = __int_as_float(mad16(bzB, cm.z)) - 8388608.0f;
+    const float exB = cxB * inv.x + (-pxB * inv.x);
+    const float eyB = cyB * inv.y + (-pyB * inv.y);
+    const float ezB = czB * inv.z + (-pzB * inv.z);
+    const float tnB = tB + gmax(gmin(exB, gmin(eyB, ezB)), 0.01f);
+    const float tB2 = (idB == 0) ? tnB : tB;
+    // front half of the step after B (needs B's block id, not B's voxel): what the next call starts from
+    const float tC = tB2 + 0.5f;
+    const float pxC = o.x + d.x * tC, pyC = o.y + d.y * tC, pzC = o.z + d.z * tC;
+    const bool outC = __float_as_uint(pxC) >= wsbits.x || __float_as_uint(pyC) >= wsbits.y || __float_as_uint(pzC) >= wsbits.z;
+    int idC = 0;
+    if (!outC && !doneA) idC = __ldg(s.world + ((f2i(pxC) >> 4) + s.wx * ((f2i(pyC) >> 4) + s.wy * (f2i(pzC) >> 4))));
+    r.px = pxC; r.py = pyC; r.pz = pzC; r.id = idC;
+    const bool hitB = voxB != 0;
+    const bool doneB = hitB || outB || !(tB2 < 128.0f);
+    t = doneA ? tA2 : tB2;
+    t_pre = doneA ? tA : tB;
+    hit = doneA ? hitA : hitB;
+    steps = doneA ? 1 : 2;
+    return doneA || doneB;
+}
+
 // A ray that ended without an in-world hit stored -t_pre.  If its last position was outside the world the
 // reference still sampled there before the bounds test (radiance.comp:212-237): take that one sample with
 // the general get_voxel.  Returns true if it hit after all; the fraction is then t_pre itself (brick 0 is

@@ -115,7 +115,12 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
 //      subgroups spread over the warps) and store_probe, one thread per probe.
 // The result does not depend on the schedule: each ray's sample sequence is a function of its
 // own (o, d, t) only, and the reduction tree is fixed.
-struct PoolRay { f3 o, d, inv; float t; int ns; i3 cm; };
+struct PoolRay {
+    f3 o, d, inv; float t; int ns; i3 cm;
+#ifdef LUMCU_ROLL
+    Roll roll;      // front half of the ray's next step (march_two_steps_rolling)
+#endif
+};
 
 // Ray slots, packed for 16-byte shared-memory accesses: a = (o.xyz, t), b = (d.xyz, inv.x),
 // c = (inv.yz).  A refill is 2 x LDS.128 + 1 x LDS.64 instead of ten scalar loads; consecutive slots
@@ -156,7 +161,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
     constexpr unsigned FULL = 0xffffffffu;
     const uint3 wsbits = {__float_as_uint(mc.wsx), __float_as_uint(mc.wsy), __float_as_uint(mc.wsz)};
     int cur = -1;
-    PoolRay q = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, 0.0f, 0, {0, 0, 0}};
+    PoolRay q = {};
     bool exhausted = false;
     int mine = first;                                              // PRIVATE: next unclaimed position
     for (;;) {
@@ -176,6 +181,9 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                     if (pos < limit) {
                         cur = src ? (int)src[pos] : pos;
                         sm.load(cur, q);
+#ifdef LUMCU_ROLL
+                        if constexpr (FAST) roll_prime(s, wsbits, q.o, q.d, q.t, q.roll);
+#endif
                     }
                 }
                 exhausted = base + cnt >= limit;
@@ -211,7 +219,11 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                 bool hit;
                 float t_end;
                 int steps;
+#ifdef LUMCU_ROLL
+                const bool done = march_two_steps_rolling(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit, steps, q.roll);
+#else
                 const bool done = march_two_steps_fast(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit, steps);
+#endif
                 q.ns += steps;
                 if (done) {
                     sm.a[cur].w = hit ? q.t : -t_end;

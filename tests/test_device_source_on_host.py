@@ -1,6 +1,6 @@
 """The CUDA kernels' per-thread arithmetic, compiled for the host, against the oracle -- no GPU needed.
 
-lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the three march variants, pending-sample resolution,
+lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the march variants -- general, fast, fused, rolling --, pending-sample resolution,
 refinement, material fetch, field gather, shading, unorm10 pack/unpack) is compiled with g++ through
 tests/device_host/cuda_host_shim.hpp and run one "thread" after another by tests/device_host/device_on_host.cpp,
 which restates only the workgroup reduction and the blend around it.  This is test infrastructure: it checks the
@@ -21,7 +21,7 @@ DEPS = [SRC, os.path.join(HERE, "device_host", "cuda_host_shim.hpp"),
 OUT = os.path.join(HERE, "_build", "libdevice_on_host.so")
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
-MODES = {"general": 0, "fast": 1, "fused": 2}
+MODES = {"general": 0, "fast": 1, "fused": 2, "rolling": 3}
 
 
 def build_host_lib(out, defines=()):
@@ -115,7 +115,7 @@ def test_synthetic_all_ray_counts(host_lib, oracle_mod, small_synth, rays):
     req = O.build_requests(small_synth["world"])[::7]
     f0 = np.random.default_rng(rays).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
     ref = O.update(sc, f0, req, 11, want_rays=True)
-    for mode in ("fast", "fused"):
+    for mode in ("fast", "fused", "rolling"):
         assert_same(run(host_lib, O, small_synth, f0, req, 11, MODES[mode], rays=rays), ref)
 
 
@@ -146,7 +146,7 @@ def test_random_small_worlds(host_lib, oracle_mod, case):
     shift = int(rng.integers(0, size))
     seed = int(rng.integers(-2 ** 31, 2 ** 31))
     ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=True)
-    modes = ("general", "fast", "fused") if not bricks[0].any() else ("general",)
+    modes = ("general", "fast", "fused", "rolling") if not bricks[0].any() else ("general",)
     for mode in modes:
         assert_same(run(host_lib, O, scn, f0, req, seed, MODES[mode], size=size, shift=shift), ref)
 

@@ -5,7 +5,7 @@
 #   under gpurun:  bash tools/next_round_sweep.sh run      -> gpurun_out/next_round_sweep.log
 set -e
 cd "$(dirname "$0")/.."
-VARIANTS=("base:" "spec2wg:-DLUMCU_SPEC2_WG" "refahead:-DLUMCU_REFINE_AHEAD" "both:-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD" "nospec2:-DLUMCU_NO_SPEC2")
+VARIANTS=("base:" "spec2wg:-DLUMCU_SPEC2_WG" "refahead:-DLUMCU_REFINE_AHEAD" "both:-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD" "roll:-DLUMCU_ROLL" "roll_refahead:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD" "nospec2:-DLUMCU_NO_SPEC2")
 if [ "$1" = build ]; then
   for v in "${VARIANTS[@]}"; do
     n=${v%%:*}; f=${v#*:}
