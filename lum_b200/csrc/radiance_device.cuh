@@ -603,4 +603,79 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
     return res;
 }
 
+// ---- glossy.frag:439-491 main() for one fragment (the body of glossy_kernel) ------------------
+struct GlossyArgs {
+    float campos[3], camdir[3], hs[3], vs[3], gld[3];   // LumcuGlossyView
+    float fw, fh;
+    int width, height;
+    const uchar4 *__restrict__ mat_norm;                // [h][w] R8G8B8A8_UINT
+    const float *__restrict__ depth;                    // [h][w]
+    float4 *__restrict__ frame;                         // [h][w]
+    uint8_t *__restrict__ covered;                      // [h][w] or null
+};
+
+// The stencil test of the pass (fillStencilGlossy.frag: discard if roughness > 0.5) is evaluated here instead of
+// by the ROP.  (px, py) is inside the frame.
+__device__ __forceinline__ void glossy_fragment(const SceneView &s, const GlossyArgs &a, int px, int py) {
+    const size_t pi = (size_t)py * a.width + px;
+    const uchar4 mn = a.mat_norm[pi];
+    const float4 m = __ldg(s.mat4 + (int)mn.x);                         // GetMat(load_mat(pix)) :443, :85-96
+    const float mr = m.x, mg = m.y, mb = m.z, me = m.w, rough = __ldg(s.materials + 6 * (int)mn.x + 5);
+    const bool cov = !(rough > 0.5f);
+    if (a.covered) a.covered[pi] = cov ? 1 : 0;
+    if (!cov) return;
+    const bool fast = s.brick0_empty && !(__ldg(s.flags) & 1u);
+    const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
+
+    f3 d = {a.camdir[0], a.camdir[1], a.camdir[2]};                     // :444
+    const float fcx = (float)px + 0.5f, fcy = (float)py + 0.5f;         // gl_FragCoord.xy
+    const float cx = fcx / a.fw * 2.0f - 1.0f, cy = fcy / a.fh * 2.0f - 1.0f;   // :446
+    const float dep = __ldg(a.depth + pi) * 1000.0f;                    // load_depth :377-382 (nearest texel = pix)
+    f3 o = {((a.campos[0] + a.hs[0] * cx) + a.vs[0] * cy) + a.camdir[0] * dep,   // get_origin_from_depth :41-47
+            ((a.campos[1] + a.hs[1] * cx) + a.vs[1] * cy) + a.camdir[1] * dep,
+            ((a.campos[2] + a.hs[2] * cx) + a.vs[2] * cy) + a.camdir[2] * dep};
+    f3 n = {(float)mn.y / 255.0f * 2.0f - 1.0f, (float)mn.z / 255.0f * 2.0f - 1.0f, (float)mn.w / 255.0f * 2.0f - 1.0f};  // load_norm :367-371
+
+    // ProcessHit(origin, direction, 0, normal, mat, ...) :454-456, :312-326
+    o = {o.x + 0.0f * d.x, o.y + 0.0f * d.y, o.z + 0.0f * d.z};
+    f3 g = gather_field(s, {(o.x + n.x * 16.0f) / 16.0f, (o.y + n.y * 16.0f) / 16.0f, (o.z + n.z * 16.0f) / 16.0f});
+    f3 refl = {1.0f * mr, 1.0f * mg, 1.0f * mb};
+    f3 light = {0.0f + refl.x * (me + g.x), 0.0f + refl.y * (me + g.y), 0.0f + refl.z * (me + g.z)};
+    {   // reflect(I, N) = I - 2 * dot(N, I) * N (GLSL 8.5), evaluated left to right (decree 14)
+        const float k = 2.0f * ((n.x * d.x + n.y * d.y) + n.z * d.z);
+        d = {d.x - k * n.x, d.y - k * n.y, d.z - k * n.z};
+    }
+
+    // trace_glossy_ray :328-360
+    const f3 inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    float t;
+    const bool hit = march_ray(s, mc, fast, o, d, inv, t);
+    __syncwarp();
+    if (hit) {
+        f3 n2;
+        float tf;
+        int vid, nr;
+        if (fast) refine_hit<false, true>(s, o, d, inv, t, n2, tf, vid, nr);
+        else refine_hit<false, false>(s, o, d, inv, t, n2, tf, vid, nr);
+        const float4 m2 = __ldg(s.mat4 + (vid & 255));
+        const float r2 = m2.x, g2 = m2.y, b2 = m2.z, e2 = m2.w;
+        const f3 x = {o.x + tf * d.x, o.y + tf * d.y, o.z + tf * d.z};
+        const f3 gg = gather_field(s, {(x.x + n2.x * 16.0f) / 16.0f, (x.y + n2.y * 16.0f) / 16.0f, (x.z + n2.z * 16.0f) / 16.0f});
+        refl = {refl.x * r2, refl.y * g2, refl.z * b2};
+        light = {light.x + refl.x * (e2 + gg.x), light.y + refl.y * (e2 + gg.y), light.z + refl.z * (e2 + gg.z)};
+    } else {
+        const float glp = -((d.x * a.gld[0] + d.y * a.gld[1]) + d.z * a.gld[2]);   // :346
+        if (glp > 0.9f) {                                                            // :347-350
+            const float w = glp - 0.9f;
+            light.x += (0.9f * 0.5f) * refl.x * w * 10.0f;
+            light.y += (0.9f * 0.5f) * refl.y * w * 10.0f;
+            light.z += (0.6f * 0.5f) * refl.z * w * 10.0f;
+        }
+        light.x += (0.53f * 0.1f) * refl.x;                                          // :353
+        light.y += (0.81f * 0.1f) * refl.y;
+        light.z += (0.92f * 0.1f) * refl.z;
+    }
+    a.frame[pi] = make_float4(light.x / 8.0f, light.y / 8.0f, light.z / 8.0f, 1.0f - rough);   // :490, encode_color :435
+}
+
 }  // namespace lumcu

@@ -117,3 +117,29 @@ extern "C" int device_on_host_update(int wx, int wy, int wz, int capacity, int b
     }
     return 0;
 }
+
+// glossy.frag for every fragment of a frame: glossy_fragment() is the body of glossy_kernel itself.
+// view = LumcuGlossyView as 17 floats: campos, camdir, horizline_scaled, vertiline_scaled, global_light_dir, frame_size.
+extern "C" int device_on_host_glossy(int wx, int wy, int wz, int capacity, int brick0_empty,
+                                     const int16_t *world, const uint8_t *bricks, const float *materials,
+                                     const uint32_t *field, const float *view, int width, int height,
+                                     const uint8_t *mat_norm, const float *depth, float *frame, uint8_t *covered) {
+    std::vector<float4> mat4(256);
+    for (int i = 0; i < 256; i++) mat4[i] = make_float4(materials[6 * i], materials[6 * i + 1], materials[6 * i + 2], materials[6 * i + 4]);
+    uint32_t flags = 0;
+    for (long long i = 0; i < (long long)wx * wy * wz; i++) if ((unsigned)world[i] >= (unsigned)capacity) flags = 1;   // validate_world_kernel
+    const SceneView s{world, bricks, materials, mat4.data(), field, wx, wy, wz, capacity, brick0_empty, &flags};
+    GlossyArgs a{};
+    for (int k = 0; k < 3; k++) {
+        a.campos[k] = view[k]; a.camdir[k] = view[3 + k]; a.hs[k] = view[6 + k]; a.vs[k] = view[9 + k]; a.gld[k] = view[12 + k];
+    }
+    a.fw = view[15]; a.fh = view[16];
+    a.width = width; a.height = height;
+    a.mat_norm = reinterpret_cast<const uchar4 *>(mat_norm);
+    a.depth = depth;
+    a.frame = reinterpret_cast<float4 *>(frame);
+    a.covered = covered;
+    for (int py = 0; py < height; py++)
+        for (int px = 0; px < width; px++) glossy_fragment(s, a, px, py);
+    return 0;
+}

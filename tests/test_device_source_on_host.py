@@ -1,7 +1,8 @@
 """The CUDA kernels' per-thread arithmetic, compiled for the host, against the oracle -- no GPU needed.
 
 lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the march variants -- general, fast, fused, rolling --, pending-sample resolution,
-refinement, material fetch, field gather, shading, unorm10 pack/unpack) is compiled with g++ through
+refinement, material fetch, field gather, shading, unorm10 pack/unpack, and glossy_fragment, the body of the
+glossy kernel) is compiled with g++ through
 tests/device_host/cuda_host_shim.hpp and run one "thread" after another by tests/device_host/device_on_host.cpp,
 which restates only the workgroup reduction and the blend around it.  This is test infrastructure: it checks the
 device SOURCE where there is no device (a change to the march that breaks parity shows up here before any GPU
@@ -161,3 +162,70 @@ def test_optin_variants_stay_bit_exact(host_lib_optin, oracle_mod, demo, small_s
         f0 = np.random.default_rng(rays + stride).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
         ref = O.update(sc, f0, req, 9, want_rays=True)
         assert_same(run(host_lib_optin, O, scn, f0, req, 9, MODES[mode], rays=rays), ref)
+
+
+# ---- the glossy pass: glossy_fragment() is the body of glossy_kernel ------------------------------------------
+def run_glossy(lib, scn, field, view, mat_norm, depth):
+    world = np.ascontiguousarray(scn["world"], np.int16)
+    bricks = np.ascontiguousarray(scn["bricks"], np.uint8)
+    mats = np.ascontiguousarray(scn["materials"], np.float32)
+    wz, wy, wx = world.shape
+    field = np.ascontiguousarray(field, np.uint32).reshape(-1)
+    mn = np.ascontiguousarray(mat_norm, np.uint8)
+    dp = np.ascontiguousarray(depth, np.float32)
+    h, w = mn.shape[:2]
+    v = np.concatenate([np.asarray(view[k], np.float32).reshape(-1) for k in
+                        ("campos", "camdir", "horizline_scaled", "vertiline_scaled", "global_light_dir", "frame_size")])
+    v = np.ascontiguousarray(v, np.float32)
+    assert v.size == 17
+    frame = np.zeros((h, w, 4), np.float32)
+    cov = np.zeros((h, w), np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.device_on_host_glossy.restype = C.c_int
+    rc = lib.device_on_host_glossy(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]),
+                                   C.c_int(int(not bricks[0].any())), p(world), p(bricks), p(mats), p(field), p(v),
+                                   C.c_int(w), C.c_int(h), p(mn), p(dp), p(frame), p(cov))
+    assert rc == 0
+    return frame, cov
+
+
+def assert_frames_equal(got, ref):
+    assert np.array_equal(got, ref)                     # -0.0 == +0.0 allowed, everything else bit for bit
+    nz = ref != 0
+    assert np.array_equal(bits(got)[nz], bits(ref)[nz])
+
+
+@pytest.mark.parametrize("optin", [False, True])
+@pytest.mark.parametrize("tag", ["demo", "demo_all", "synth"])
+def test_glossy_fragment_matches_oracle(host_lib, host_lib_optin, oracle_mod, tag, optin):
+    """The cases of tests/test_glossy_gpu.py on the host build (default and opt-in march)."""
+    from glossy_cases import make_case
+    O = oracle_mod
+    c = make_case(O, tag)
+    ref = O.glossy(c["scene"], c["field"], c["view"], c["mat_norm"], c["depth"])
+    got, cov = run_glossy(host_lib_optin if optin else host_lib, c["scn"], c["field"], c["view"], c["mat_norm"], c["depth"])
+    assert np.array_equal(cov, ref["covered"]) and cov.any()
+    assert_frames_equal(got, ref["frame"])
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_glossy_fragment_random_gbuffers(host_lib, host_lib_optin, oracle_mod, seed):
+    """Arbitrary G-buffers (origins inside solids and outside the world, unnormalised normals); seed 3 loads a
+    brick 0 (general march)."""
+    from glossy_cases import make_case
+    O = oracle_mod
+    c = make_case(O, "synth")
+    scn = {k: v.copy() for k, v in c["scn"].items()}
+    rng = np.random.default_rng(seed)
+    if seed == 3:
+        scn["bricks"][0] = (rng.random((16, 16, 16)) < 0.01) * 5
+    sc = O.Scene(scn["world"], scn["bricks"], scn["materials"])
+    h, w = 37 + seed, 61 - seed
+    mn = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    dp = rng.random((h, w), dtype=np.float32) * np.float32(0.6)
+    view = O.camera_view((rng.random(3) * 300 - 50), (0.3 + seed, 0.9 - seed, -0.6), w, h, pixels_in_voxel=0.2)
+    ref = O.glossy(sc, c["field"], view, mn, dp)
+    for lib in (host_lib, host_lib_optin):
+        got, cov = run_glossy(lib, scn, c["field"], view, mn, dp)
+        assert np.array_equal(cov, ref["covered"]) and cov.any()
+        assert_frames_equal(got, ref["frame"])
