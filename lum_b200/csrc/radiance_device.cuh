@@ -678,4 +678,41 @@ __device__ __forceinline__ void glossy_fragment(const SceneView &s, const Glossy
     a.frame[pi] = make_float4(light.x / 8.0f, light.y / 8.0f, light.z / 8.0f, 1.0f - rough);   // :490, encode_color :435
 }
 
+// ---- shaders/map.comp:32-67 for one invocation (the body of map_model_kernel) ----------------
+struct MapArgs {
+    float m[16];                 // inverse_trans, column-major (glm mat4)
+    int shift[3];
+    int ext[3];                  // invocations per axis = 4*ceil(area/4)
+    int msx, msy, msz;           // model size
+    int static_count;
+};
+
+// (gx, gy, gz) = gl_GlobalInvocationID inside the dispatched area.
+__device__ __forceinline__ void map_model_invocation(const int16_t *__restrict__ world, uint8_t *__restrict__ bricks,
+                                                     const uint8_t *__restrict__ model, int wx, int wy, int wz,
+                                                     int capacity, const MapArgs &a, int gx, int gy, int gz) {
+    // world_voxel = vec3(gid)/1.0 + vec3(0.5) + vec3(shift)      (:41-43)
+    const float px = ((float)gx + 0.5f) + (float)a.shift[0];
+    const float py = ((float)gy + 0.5f) + (float)a.shift[1];
+    const float pz = ((float)gz + 0.5f) + (float)a.shift[2];
+    if (px < 0.0f || py < 0.0f || pz < 0.0f) return;          // decree 11: below-world invocations alias + race in the reference
+    const int ix = f2i(px), iy = f2i(py), iz = f2i(pz);       // ivec3(world_voxel) :44
+    // model_voxel = (inverse_trans * vec4(world_voxel,1)).xyz   (:50), columns summed 0,1,2,3
+    const float mx = ((a.m[0] * px + a.m[4] * py) + a.m[8] * pz) + a.m[12] * 1.0f;
+    const float my = ((a.m[1] * px + a.m[5] * py) + a.m[9] * pz) + a.m[13] * 1.0f;
+    const float mz = ((a.m[2] * px + a.m[6] * py) + a.m[10] * pz) + a.m[14] * 1.0f;
+    const int jx = f2i(mx), jy = f2i(my), jz = f2i(mz);       // ivec3(model_voxel) :51
+    const int bx = sdiv16(ix), by = sdiv16(iy), bz = sdiv16(iz);   // iworld_voxel/16 :53
+    int id = 0;
+    if ((unsigned)bx < (unsigned)wx && (unsigned)by < (unsigned)wy && (unsigned)bz < (unsigned)wz)
+        id = world[bx + wx * (by + wy * bz)];
+    if (id >= a.static_count && id < capacity) {              // :62 (stores outside the atlas are dropped)
+        int v = 0;
+        if ((unsigned)jx < (unsigned)a.msx && (unsigned)jy < (unsigned)a.msy && (unsigned)jz < (unsigned)a.msz)
+            v = model[jx + a.msx * (jy + a.msy * jz)];
+        if (v != 0)
+            bricks[(size_t)id * 4096u + (size_t)(((ix & 15) << 8) | ((iy & 15) << 4) | (iz & 15))] = (uint8_t)v;
+    }
+}
+
 }  // namespace lumcu

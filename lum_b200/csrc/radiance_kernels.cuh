@@ -553,14 +553,6 @@ __global__ void copy_bricks_kernel(uint8_t *__restrict__ bricks, const int2 *__r
     reinterpret_cast<uint4 *>(bricks + (size_t)pr.y * 4096u)[threadIdx.x] = v;
 }
 
-struct MapArgs {
-    float m[16];                 // inverse_trans, column-major (glm mat4)
-    int shift[3];
-    int ext[3];                  // invocations per axis = 4*ceil(area/4)
-    int msx, msy, msz;           // model size
-    int static_count;
-};
-
 // shaders/map.comp:32-67.  One thread per invocation; z is the fastest thread index so that the
 // conditional stores of a warp fall into one 16-byte z-row of a brick where possible.
 __global__ void map_model_kernel(const int16_t *__restrict__ world, uint8_t *__restrict__ bricks,
@@ -569,28 +561,7 @@ __global__ void map_model_kernel(const int16_t *__restrict__ world, uint8_t *__r
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int gz = (int)(i % a.ext[2]), gy = (int)((i / a.ext[2]) % a.ext[1]), gx = (int)(i / ((long long)a.ext[2] * a.ext[1]));
-    // world_voxel = vec3(gid)/1.0 + vec3(0.5) + vec3(shift)      (:41-43)
-    const float px = ((float)gx + 0.5f) + (float)a.shift[0];
-    const float py = ((float)gy + 0.5f) + (float)a.shift[1];
-    const float pz = ((float)gz + 0.5f) + (float)a.shift[2];
-    if (px < 0.0f || py < 0.0f || pz < 0.0f) return;          // decree 11: below-world invocations alias + race in the reference
-    const int ix = f2i(px), iy = f2i(py), iz = f2i(pz);       // ivec3(world_voxel) :44
-    // model_voxel = (inverse_trans * vec4(world_voxel,1)).xyz   (:50), columns summed 0,1,2,3
-    const float mx = ((a.m[0] * px + a.m[4] * py) + a.m[8] * pz) + a.m[12] * 1.0f;
-    const float my = ((a.m[1] * px + a.m[5] * py) + a.m[9] * pz) + a.m[13] * 1.0f;
-    const float mz = ((a.m[2] * px + a.m[6] * py) + a.m[10] * pz) + a.m[14] * 1.0f;
-    const int jx = f2i(mx), jy = f2i(my), jz = f2i(mz);       // ivec3(model_voxel) :51
-    const int bx = sdiv16(ix), by = sdiv16(iy), bz = sdiv16(iz);   // iworld_voxel/16 :53
-    int id = 0;
-    if ((unsigned)bx < (unsigned)wx && (unsigned)by < (unsigned)wy && (unsigned)bz < (unsigned)wz)
-        id = world[bx + wx * (by + wy * bz)];
-    if (id >= a.static_count && id < capacity) {              // :62 (stores outside the atlas are dropped)
-        int v = 0;
-        if ((unsigned)jx < (unsigned)a.msx && (unsigned)jy < (unsigned)a.msy && (unsigned)jz < (unsigned)a.msz)
-            v = model[jx + a.msx * (jy + a.msy * jz)];
-        if (v != 0)
-            bricks[(size_t)id * 4096u + (size_t)(((ix & 15) << 8) | ((iy & 15) << 4) | (iz & 15))] = (uint8_t)v;
-    }
+    map_model_invocation(world, bricks, model, wx, wy, wz, capacity, a, gx, gy, gz);
 }
 
 // ---- request-list builder (internal_render.cpp:1142-1169) ------------------------------

@@ -143,3 +143,24 @@ extern "C" int device_on_host_glossy(int wx, int wy, int wz, int capacity, int b
         for (int px = 0; px < width; px++) glossy_fragment(s, a, px, py);
     return 0;
 }
+
+// map.comp for one model: the host half of lumcu_map_model (invocations per axis = 4*ceil(area/4), z fastest) around
+// map_model_invocation(), the body of map_model_kernel.  bricks is modified in place.
+extern "C" int device_on_host_map_model(int wx, int wy, int wz, int capacity, const int16_t *world, uint8_t *bricks,
+                                        const uint8_t *model, int sx, int sy, int sz, const float *inv16,
+                                        const int32_t *shift, const int32_t *area, int static_count) {
+    MapArgs a;
+    for (int i = 0; i < 16; i++) a.m[i] = inv16[i];
+    for (int k = 0; k < 3; k++) {
+        a.shift[k] = shift[k];
+        const int groups = (area[k] + 3) / 4;
+        a.ext[k] = groups > 0 ? groups * 4 : 0;
+    }
+    a.msx = sx; a.msy = sy; a.msz = sz;
+    a.static_count = static_count;
+    for (int gx = 0; gx < a.ext[0]; gx++)
+        for (int gy = 0; gy < a.ext[1]; gy++)
+            for (int gz = 0; gz < a.ext[2]; gz++)
+                map_model_invocation(world, bricks, model, wx, wy, wz, capacity, a, gx, gy, gz);
+    return 0;
+}

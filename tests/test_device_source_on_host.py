@@ -1,8 +1,8 @@
 """The CUDA kernels' per-thread arithmetic, compiled for the host, against the oracle -- no GPU needed.
 
 lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the march variants -- general, fast, fused, rolling --, pending-sample resolution,
-refinement, material fetch, field gather, shading, unorm10 pack/unpack, and glossy_fragment, the body of the
-glossy kernel) is compiled with g++ through
+refinement, material fetch, field gather, shading, unorm10 pack/unpack, glossy_fragment and map_model_invocation,
+the bodies of the glossy and map kernels) is compiled with g++ through
 tests/device_host/cuda_host_shim.hpp and run one "thread" after another by tests/device_host/device_on_host.cpp,
 which restates only the workgroup reduction and the blend around it.  This is test infrastructure: it checks the
 device SOURCE where there is no device (a change to the march that breaks parity shows up here before any GPU
@@ -229,3 +229,51 @@ def test_glossy_fragment_random_gbuffers(host_lib, host_lib_optin, oracle_mod, s
         got, cov = run_glossy(lib, scn, c["field"], view, mn, dp)
         assert np.array_equal(cov, ref["covered"]) and cov.any()
         assert_frames_equal(got, ref["frame"])
+
+
+# ---- map.comp: map_model_invocation() is the body of map_model_kernel -----------------------------------------
+def _quat_yaw(a):
+    import math
+    return (np.float32(math.cos(a / 2)), np.float32(0), np.float32(0), np.float32(math.sin(a / 2)))
+
+
+def _quat_axis(axis, a):
+    import math
+    ax = np.asarray(axis, np.float64); ax = ax / np.linalg.norm(ax)
+    s = math.sin(a / 2)
+    return tuple(np.float32(v) for v in (math.cos(a / 2), ax[0] * s, ax[1] * s, ax[2] * s))
+
+
+MAP_PLACEMENTS = [           # the cases of tests/test_feeders_gpu.py::test_map_model_matches_oracle
+    ("identity", (1, 0, 0, 0), (13.1 * 16, 14.1 * 16, 3.1 * 16)),
+    ("yaw", _quat_yaw(0.7), (300.0, 310.0, 40.0)),
+    ("tilted", _quat_axis((1, 2, 3), 1.1), (400.5, 200.25, 100.75)),
+    ("low corner, partly outside", _quat_yaw(-2.1), (12.0, 17.0, 30.0)),
+    ("high corner, partly outside", _quat_axis((0, 1, 0), 0.3), (750.0, 755.0, 245.0)),
+    ("fully outside", (1, 0, 0, 0), (-400.0, -400.0, -400.0)),
+]
+
+
+@pytest.mark.parametrize("name,rot,shift", MAP_PLACEMENTS, ids=[p[0] for p in MAP_PLACEMENTS])
+def test_map_model_invocation_matches_oracle(host_lib, oracle_mod, demo, name, rot, shift):
+    O = oracle_mod
+    host_lib.device_on_host_map_model.restype = C.c_int
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)
+    for mname in ("model_tank_body", "model_robot"):
+        model = np.ascontiguousarray(demo[mname], np.uint8)
+        sz, sy, sx = model.shape
+        pl = O.place_model(rot, shift, (sx, sy, sz), (48, 48, 16))
+        cur, src, dst = O.blockify(demo["world"], 15, [pl])
+        bricks = np.zeros((512, 16, 16, 16), np.uint8); bricks[:15] = demo["bricks"]
+        O.copy_bricks(bricks, src, dst)
+        got = bricks.copy()
+        O.map_model(cur, bricks, model, pl, 15)
+        cur = np.ascontiguousarray(cur, np.int16)
+        inv = np.array(pl.inverse_trans, np.float32)
+        sh = np.array(list(pl.map_shift), np.int32)
+        ar = np.array(list(pl.map_area), np.int32)
+        rc = host_lib.device_on_host_map_model(C.c_int(48), C.c_int(48), C.c_int(16), C.c_int(512), p_(cur), p_(got),
+                                               p_(model), C.c_int(sx), C.c_int(sy), C.c_int(sz), p_(inv), p_(sh), p_(ar),
+                                               C.c_int(15))
+        assert rc == 0
+        assert np.array_equal(got, bricks), mname
