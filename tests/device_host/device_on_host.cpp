@@ -77,9 +77,10 @@ extern "C" int device_on_host_update(int wx, int wy, int wz, int capacity, int b
     const long long cells = (long long)wx * wy * wz;
     for (long long i = 0; i < cells; i++) field_new[i] = field_old[i];
     const int SUB = R < 32 ? R : 32, NSUB = R / SUB;
-    std::vector<f3> light(R);
     const long long nwg = nreq / size;
+#pragma omp parallel for schedule(dynamic, 64)      // workgroups are independent (Jacobi update); built with -fopenmp
     for (long long w = 0; w < nwg; w++) {
+        std::vector<f3> light(R);
         const int16_t *rq = requests + 4 * (w * size + shift);
         for (int ray = 0; ray < R; ray++) {
             const uint32_t gid_x = (uint32_t)(w * R + ray);

@@ -32,7 +32,7 @@ def build_host_lib(out, defines=()):
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS + [__file__]):
         # -ffp-contract=off = nvcc -fmad=false: one rounding per written operation (DESIGN.md decree 4)
         r = subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                            "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines], "-I", CUDA_INC, "-o", out, SRC],
+                            "-fopenmp", "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines], "-I", CUDA_INC, "-o", out, SRC],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
     lib = C.CDLL(out)
@@ -118,6 +118,19 @@ def test_synthetic_all_ray_counts(host_lib, oracle_mod, small_synth, rays):
     ref = O.update(sc, f0, req, 11, want_rays=True)
     for mode in ("fast", "fused", "rolling"):
         assert_same(run(host_lib, O, small_synth, f0, req, 11, MODES[mode], rays=rays), ref)
+
+
+def test_synthetic_64x64x16_full_update(host_lib, oracle_mod):
+    """BASELINE configs[4]'s smallest world, whole (65,456 probes, 4.2 M rays), fused and rolling march."""
+    from lum_b200 import scenes
+    O = oracle_mod
+    syn = scenes.synthetic_scene(64, 64, 16)
+    sc = scene_of(O, syn)
+    req = O.build_requests(syn["world"])
+    f0 = np.random.default_rng(0).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 7, want_rays=True)
+    for mode in ("fused", "rolling"):
+        assert_same(run(host_lib, O, syn, f0, req, 7, MODES[mode]), ref)
 
 
 @pytest.mark.parametrize("case", range(24))
