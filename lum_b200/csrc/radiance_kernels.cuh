@@ -275,6 +275,15 @@ __device__ __forceinline__ void pool_shade(PoolShared<NR, DEBUG> &sm, const Scen
     }
 }
 
+// Named barrier 1: the tail warps of a CTA among themselves (count = 32 x tail warps).
+__device__ __forceinline__ void tail_barrier_sync(int count) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory");
+#elif defined(LUMCU_HOST_EMU)     // tests/device_host/simt_emu.hpp: the kernels run thread by thread on the host (tests only)
+    lumcu_host_named_barrier(1, count);
+#endif
+}
+
 #ifndef LUMCU_TAILDIV
 #define LUMCU_TAILDIV 48       // stragglers per tail warp
 #endif
@@ -351,11 +360,11 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
         for (;;) {
             const int wr = rd == 1 ? 2 : 1;
             if (tid == 0) { sm_next = 0; sm_park[wr] = 0; }
-            asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
+            tail_barrier_sync(tail_threads);
             const int parts = max(1, min(tail_warps, (limit + LUMCU_TAILDIV - 1) / LUMCU_TAILDIV));
             if (warp < parts)
                 pool_march<NR, PARK, DEBUG, false, FAST>(sm, s, mc, &sm_next, 0, sm_list[rd], limit, sm_list[wr], &sm_park[wr], parts > 1, lane);
-            asm volatile("bar.sync 1, %0;" ::"r"(tail_threads) : "memory");
+            tail_barrier_sync(tail_threads);
             const int parked = sm_park[wr];
             if (parked == 0) break;
             limit = parked;

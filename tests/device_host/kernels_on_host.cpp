@@ -1,0 +1,85 @@
+// kernels_on_host.cpp -- TEST INFRASTRUCTURE ONLY (see simt_emu.hpp).
+// The radiance update as lumcu.cu's do_update() launches it -- trace kernel (pooled or one workgroup per CTA), then the
+// commit kernel -- with the kernels of lum_b200/csrc/radiance_kernels.cuh themselves running on the host emulator.
+#include "simt_emu.hpp"
+#include "../../lum_b200/csrc/radiance_kernels.cuh"
+
+using namespace lumcu;
+
+#ifndef LUMCU_RPT
+#define LUMCU_RPT 3
+#endif
+
+template <int R, int T>
+static void launch_pool(const SceneView &s, const UpdateArgs &a, long long nwg) {
+    constexpr int ppc = LUMCU_RPT * T / R;
+    emu_launch((unsigned)((nwg + ppc - 1) / ppc), 1, T, [&] { radiance_update_pool_kernel<R, T, LUMCU_RPT, true>(s, a); });
+}
+template <int R>
+static void launch_wg(const SceneView &s, const UpdateArgs &a, long long nwg) {
+    emu_launch((unsigned)nwg, 1, R, [&] { radiance_update_wg_kernel<R, true>(s, a); });
+}
+
+// variant: 0 = one workgroup per CTA, 1 = pooled.  il_rank / il_n: interleaved shard (il_n = 1: everything).
+extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
+                                      const int16_t *world, const uint8_t *bricks, const float *materials,
+                                      const uint32_t *field_old, uint32_t *field_new,
+                                      const int16_t *requests, long long nreq, int time_seed, int size, int shift,
+                                      const float *table, const float *sun3, int variant, int il_rank, int il_n,
+                                      float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals) {
+    if (size < 1 || shift < 0 || shift >= size || il_n < 1 || il_rank < 0 || il_rank >= il_n) return -1;
+    std::vector<float4> mat4(256);
+    for (int i = 0; i < 256; i++) mat4[i] = make_float4(materials[6 * i], materials[6 * i + 1], materials[6 * i + 2], materials[6 * i + 4]);
+    const long long cells = (long long)wx * wy * wz;
+    uint32_t flags = 0;
+    emu_launch(2, 1, 64, [&] { validate_world_kernel(world, cells, capacity, &flags); });
+    const SceneView s{world, bricks, materials, mat4.data(), field_old, wx, wy, wz, capacity, brick0_empty, &flags};
+    const long long nwg_all = nreq / size;
+    std::vector<uint32_t> staged((size_t)std::max<long long>(nwg_all, 1));
+    UpdateArgs a{};
+    a.requests = reinterpret_cast<const short4 *>(requests);
+    a.dir_table = table;
+    a.staged = staged.data();
+    a.dbg_pre_blend = pre_blend; a.dbg_samples = ray_samples; a.dbg_hits = ray_hits; a.dbg_totals = totals;
+    a.wg_begin = 0; a.wg_end = nwg_all;
+    constexpr int IL_CHUNK = 3072;
+    a.il_chunk = IL_CHUNK; a.il_rank = il_rank; a.il_n = il_n;
+    a.time_seed = time_seed; a.size = size; a.shift = shift;
+    a.z_begin = -32768; a.z_end = 32768;
+    a.reactiveness = reactiveness;
+    a.sun_x = sun3[0]; a.sun_y = sun3[1]; a.sun_z = sun3[2];
+    totals[0] = totals[1] = 0;
+    // workgroups this launch traces (lumcu.cu: il_count)
+    long long nwg = nwg_all;
+    if (il_n > 1) {
+        const long long full = nwg_all / IL_CHUNK, rem = nwg_all % IL_CHUNK;
+        nwg = (full / il_n) * IL_CHUNK + ((full % il_n) > il_rank ? IL_CHUNK : 0) + ((full % il_n) == il_rank ? rem : 0);
+    }
+    for (long long i = 0; i < cells; i++) field_new[i] = field_old[i];
+    if (nwg <= 0) return 0;
+    if (variant == 1) {
+        switch (R) {
+            case 16: launch_pool<16, 128>(s, a, nwg); break;
+            case 32: launch_pool<32, 128>(s, a, nwg); break;
+            case 64: launch_pool<64, 128>(s, a, nwg); break;
+            case 128: launch_pool<128, 128>(s, a, nwg); break;
+            case 256: launch_pool<256, 256>(s, a, nwg); break;
+            default: return -1;
+        }
+    } else {
+        switch (R) {
+            case 16: launch_wg<16>(s, a, nwg); break;
+            case 32: launch_wg<32>(s, a, nwg); break;
+            case 64: launch_wg<64>(s, a, nwg); break;
+            case 128: launch_wg<128>(s, a, nwg); break;
+            case 256: launch_wg<256>(s, a, nwg); break;
+            default: return -1;
+        }
+    }
+    const Interleave il{IL_CHUNK, il_rank, il_n};
+    const int ct = 64;
+    emu_launch((unsigned)((nwg + ct - 1) / ct), 1, ct, [&] {
+        commit_kernel(field_new, staged.data(), a.requests, 0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, il);
+    });
+    return 0;
+}

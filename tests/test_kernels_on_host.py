@@ -1,0 +1,145 @@
+"""The CUDA kernels themselves on a host SIMT emulator, against the oracle -- no GPU needed.
+
+tests/device_host/simt_emu.hpp runs the __global__ functions of lum_b200/csrc/radiance_kernels.cuh with one OS thread per
+CUDA thread (warp collectives as rendezvous, __syncthreads / the named barrier as counting barriers, __shared__ as a
+static of the one resident CTA).  tests/device_host/kernels_on_host.cpp launches them the way lumcu.cu's do_update()
+does: validate_world_kernel, the trace kernel (pooled: ray pool, lane refill, parking, tail passes, reduction; or one
+workgroup per CTA), commit_kernel.  Where tests/test_device_source_on_host.py checks the per-thread arithmetic, this
+checks the ORCHESTRATION -- which ray lands in which slot, what a parked ray carries, who reduces what -- before any GPU
+time is spent.  Test infrastructure only; the emulator is slow (a barrier per collective), so the scenes are small.
+Bar: bit-exact, like on the GPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_device_source_on_host import CUDA_INC, HERE, assert_same, scene_of
+
+SRC = os.path.join(HERE, "device_host", "kernels_on_host.cpp")
+DEPS = [SRC, __file__] + [os.path.join(HERE, "device_host", f) for f in ("simt_emu.hpp", "cuda_host_shim.hpp")] + \
+       [os.path.join(HERE, "..", "lum_b200", "csrc", f) for f in ("radiance_device.cuh", "radiance_kernels.cuh")]
+OUT = os.path.join(HERE, "_build", "libkernels_on_host.so")
+
+POOL, WG = 1, 0
+
+
+def build(out, defines=()):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in DEPS):
+        r = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off",
+                            "-fno-fast-math", "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines], "-I", CUDA_INC,
+                            "-o", out, SRC], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    lib = C.CDLL(out)
+    lib.kernels_on_host_update.restype = C.c_int
+    return lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build(OUT)
+
+
+@pytest.fixture(scope="module")
+def emu_optin():
+    """The compile-time variants that are not the default yet, all at once: here their kernel
+    integration runs -- e.g. the rolling block-id fetch being primed at every refill and again for a parked ray."""
+    return build(OUT.replace(".so", "_optin.so"), ("LUMCU_ROLL", "LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD"))
+
+
+def run(lib, O, scn, f0, req, seed, variant, rays=64, size=1, shift=0, reactiveness=0.01):
+    world = np.ascontiguousarray(scn["world"], np.int16)
+    bricks = np.ascontiguousarray(scn["bricks"], np.uint8)
+    mats = np.ascontiguousarray(scn["materials"], np.float32)
+    wz, wy, wx = world.shape
+    req = np.ascontiguousarray(req, np.int16).reshape(-1, 4)
+    nwg = len(req) // size
+    f0 = np.ascontiguousarray(f0, np.uint32).reshape(-1)
+    f1 = np.empty_like(f0)
+    pre = np.zeros((nwg, 3), np.float32)
+    rs = np.zeros(nwg * rays, np.uint32)
+    rh = np.zeros(nwg * rays, np.uint8)
+    tot = np.zeros(2, np.uint64)
+    table = np.ascontiguousarray(O.direction_table(rays), np.float32)
+    sun = np.ascontiguousarray(O.sun_dir(), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.kernels_on_host_update(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]),
+                                    C.c_int(int(not bricks[0].any())), C.c_int(rays), C.c_float(reactiveness),
+                                    p(world), p(bricks), p(mats), p(f0), p(f1), p(req), C.c_longlong(len(req)),
+                                    C.c_int(seed), C.c_int(size), C.c_int(shift), p(table), p(sun), C.c_int(variant),
+                                    C.c_int(0), C.c_int(1), p(pre), p(rs), p(rh), p(tot))
+    assert rc == 0
+    return dict(field=f1, pre_blend=pre, ray_samples=rs, ray_hits=rh, totals=(int(tot[0]), int(tot[1])))
+
+
+def check(lib, O, scn, req, seed, variant, rays=64, size=1, shift=0, field_seed=3):
+    sc = scene_of(O, scn, rays=rays)
+    f0 = np.random.default_rng(field_seed).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=True)
+    got = run(lib, O, scn, f0, req, seed, variant, rays=rays, size=size, shift=shift)
+    assert_same(got, ref)
+    assert got["totals"] == ref["totals"][:2]
+
+
+@pytest.mark.parametrize("variant", [POOL, WG], ids=["pooled", "workgroup"])
+def test_demo_world_kernels(emu, oracle_mod, demo, variant):
+    """61 probes of the demo world (a ragged last batch for the pooled kernel: 10 full CTAs + 1 probe)."""
+    O = oracle_mod
+    check(emu, O, demo, O.build_requests(demo["world"])[1000:1061], 5, variant)
+
+
+@pytest.mark.parametrize("rays", [16, 64, 256])
+def test_dense_world_pooled_kernel_ray_counts(emu, oracle_mod, small_synth, rays):
+    """The C4 generator's dense world: long and short rays side by side, so lanes refill, warps park and the tail
+    warps run; 16 (24 probes per CTA), 64 and 256 rays per probe (256-thread CTAs)."""
+    O = oracle_mod
+    n = {16: 50, 64: 20, 256: 7}[rays]
+    check(emu, O, small_synth, O.build_requests(small_synth["world"])[::97][:n], 11, POOL, rays=rays)
+
+
+def test_dense_world_workgroup_kernel(emu, oracle_mod, small_synth):
+    O = oracle_mod
+    check(emu, O, small_synth, O.build_requests(small_synth["world"])[::131][:24], 2, WG)
+    check(emu, O, small_synth, O.build_requests(small_synth["world"])[::131][:24], 2, WG, rays=16)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 7, 9, 15])
+def test_fuzz_worlds_kernels(emu, oracle_mod, case):
+    """Cases of the GPU fuzz (tests/test_parity_gpu.py::test_random_small_worlds): odd sizes, out-of-world probes,
+    magicSize dispatch, a loaded brick 0 (cases 0, 9, 15) and an id outside the palette (7, 15): the general march,
+    selected by the host flag and by validate_world_kernel's device flag."""
+    O = oracle_mod
+    rng = np.random.default_rng(1000 + case)
+    wx, wy, wz = (int(v) for v in rng.integers(1, [9, 8, 5]))
+    P = int(rng.integers(2, 41))
+    bricks = ((rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))).astype(np.uint8)
+    if case % 3:
+        bricks[0] = 0
+    world = ((rng.random((wz, wy, wx)) < rng.choice([0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
+    if case % 8 == 7:
+        world.reshape(-1)[0] = P + 3
+    mats = rng.random((256, 6)).astype(np.float32)
+    mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
+    scn = dict(world=world, bricks=bricks, materials=mats)
+    inside = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+    outside = np.array([(-1, 0, 0, 0), (wx, 0, 0, 0), (0, -2, wz, 0), (wx + 3, wy + 1, -1, 0)], np.int16)
+    req = np.concatenate([inside, outside])
+    req = req[rng.permutation(len(req))][: max(1, min(40, int(rng.integers(1, len(req) + 1))))]
+    size = min(int(rng.integers(1, 4)), len(req))
+    shift = int(rng.integers(0, size))
+    seed = int(rng.integers(-2 ** 31, 2 ** 31))
+    for variant in (POOL, WG):
+        check(emu, O, scn, req, seed, variant, size=size, shift=shift, field_seed=case)
+
+
+@pytest.mark.parametrize("variant", [POOL, WG], ids=["pooled", "workgroup"])
+def test_optin_variants_kernel_integration(emu_optin, oracle_mod, demo, small_synth, variant):
+    """-DLUMCU_ROLL -DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD (off by default) through the real kernels."""
+    O = oracle_mod
+    check(emu_optin, O, demo, O.build_requests(demo["world"])[1000:1043], 5, variant)
+    check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:20], 11, variant)
