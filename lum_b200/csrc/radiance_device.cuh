@@ -134,11 +134,9 @@ struct RayResult {
 // ---- ray setup (radiance.comp:370-381) ---------------------------------------------------
 // gid_x = gl_GlobalInvocationID.x, ray = gid_x % R, fib = direction table entry of `ray`.
 // Outputs origin o, direction d and inv = 1/d (radiance.comp:198).
-__device__ __forceinline__ void setup_ray(int px, int py, int pz, uint32_t gid_x, int ray, f3 fib,
-                                          int time_seed, f3 &o, f3 &d, f3 &inv) {
-    uint32_t sx = gid_x + (uint32_t)time_seed, sy = (uint32_t)time_seed, sz = (uint32_t)time_seed;
-    f3 r1 = hash33(sx, sy, sz);
-    f3 r2 = hash33(sx + 1u, sy, sz);
+// r1, r2 = the two Random3D() draws of the ray (radiance.comp:60-66), already computed.
+__device__ __forceinline__ void setup_ray_from_draws(int px, int py, int pz, int ray, f3 fib, f3 r1, f3 r2,
+                                                     f3 &o, f3 &d, f3 &inv) {
     f3 j = {fib.x + 0.1f * ((r1.x - 0.5f) * 2.0f), fib.y + 0.1f * ((r1.y - 0.5f) * 2.0f),
             fib.z + 0.1f * ((r1.z - 0.5f) * 2.0f)};
     float len = sqrtf(j.x * j.x + j.y * j.y + j.z * j.z);
@@ -148,6 +146,13 @@ __device__ __forceinline__ void setup_ray(int px, int py, int pz, uint32_t gid_x
     o.x += (r2.x - 0.5f) * 2.0f; o.y += (r2.y - 0.5f) * 2.0f; o.z += (r2.z - 0.5f) * 2.0f;
     if (ray & 1) { d.x = -d.x; d.y = -d.y; d.z = -d.z; }
     inv = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+}
+__device__ __forceinline__ void setup_ray(int px, int py, int pz, uint32_t gid_x, int ray, f3 fib,
+                                          int time_seed, f3 &o, f3 &d, f3 &inv) {
+    uint32_t sx = gid_x + (uint32_t)time_seed, sy = (uint32_t)time_seed, sz = (uint32_t)time_seed;
+    f3 r1 = hash33(sx, sy, sz);
+    f3 r2 = hash33(sx + 1u, sy, sz);
+    setup_ray_from_draws(px, py, pz, ray, fib, r1, r2, o, d, inv);
 }
 
 // ---- one iteration of the coarse march (radiance.comp:205-244) ----------------------------

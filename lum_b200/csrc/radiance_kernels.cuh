@@ -328,6 +328,40 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     __syncthreads();
 
     // ---- phase A: setup ----
+#ifdef LUMCU_HASH_SHARE   // opt-in until measured
+    // The second draw of ray g is the first draw of ray g + 1 (the RNG state only differs in x = gid + seed, and the
+    // second draw increments x): a warp that sets up the 32*RPT contiguous rays of its own pass-0 slice needs RPT + 1
+    // hash evaluations per lane instead of 2*RPT, and takes each ray's second draw from its neighbour lane (lane 31:
+    // from lane 0's next round).  The slice is then written and read by this warp only: __syncwarp, not __syncthreads.
+    {
+        constexpr int ROUNDS = NR / NW / 32;
+        const int first = warp * (NR / NW);
+        const uint32_t useed = (uint32_t)a.time_seed;
+        f3 hk = hash33((uint32_t)(wg0 * R + first + lane) + useed, useed, useed);
+#pragma unroll 1
+        for (int k = 0; k < ROUNDS; k++) {
+            const int r = first + 32 * k + lane;
+            const f3 hn = hash33((uint32_t)(wg0 * R + r + 32) + useed, useed, useed);      // this lane's draw of the next round
+            const f3 give = lane == 0 ? hn : hk;
+            const f3 r2 = {__shfl_sync(FULL, give.x, (lane + 1) & 31), __shfl_sync(FULL, give.y, (lane + 1) & 31),
+                           __shfl_sync(FULL, give.z, (lane + 1) & 31)};
+            if (r < nrays) {
+                const int pr = r / R, ray = r % R;
+                const short4 rq = sm_req[pr];
+                const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
+                f3 o, d, inv;
+                setup_ray_from_draws(rq.x, rq.y, rq.z, ray, fib, hk, r2, o, d, inv);
+                sm.a[r] = make_float4(o.x, o.y, o.z, 0.0f);
+                sm.b[r] = make_float4(d.x, d.y, d.z, inv.x);
+                sm.c[r] = make_float2(inv.y, inv.z);
+                sm.done[r] = 1;
+                if constexpr (DEBUG) sm.ns[r] = 0;
+            }
+            hk = hn;
+        }
+    }
+    __syncwarp();
+#else
     for (int r = tid; r < nrays; r += THREADS) {
         const int pr = r / R, ray = r % R;
         const short4 rq = sm_req[pr];
@@ -342,6 +376,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
         if constexpr (DEBUG) sm.ns[r] = 0;
     }
     __syncthreads();
+#endif
 
     // ---- phase B, pass 0: every warp marches ----
     const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};

@@ -28,4 +28,6 @@ static inline int __float2int_rn(float f) {
     return (int)std::nearbyintf(f);
 }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
-static inline void __syncwarp() {}
+#ifndef LUMCU_HOST_EMU
+static inline void __syncwarp() {}     // one thread at a time
+#endif

@@ -81,6 +81,10 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int k) {
     const int src = (int)(threadIdx.x & 31) - k;
     return (src >= 0) ? emu_from<T>(all[src]) : v;
 }
+static inline void __syncwarp(unsigned = 0xffffffffu) {
+    EmuWarp &w = emu_cta->warps[threadIdx.x >> 5];
+    w.bar.arrive_and_wait(w.size);
+}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
 // ---- CTA barriers --------------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ def emu():
 def emu_optin():
     """The compile-time variants that are not the default yet, all at once: here their kernel
     integration runs -- e.g. the rolling block-id fetch being primed at every refill and again for a parked ray."""
-    return build(OUT.replace(".so", "_optin.so"), ("LUMCU_ROLL", "LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD"))
+    return build(OUT.replace(".so", "_optin.so"), ("LUMCU_ROLL", "LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD", "LUMCU_HASH_SHARE"))
 
 
 def run(lib, O, scn, f0, req, seed, variant, rays=64, size=1, shift=0, reactiveness=0.01):
@@ -139,7 +139,11 @@ def test_fuzz_worlds_kernels(emu, oracle_mod, case):
 
 @pytest.mark.parametrize("variant", [POOL, WG], ids=["pooled", "workgroup"])
 def test_optin_variants_kernel_integration(emu_optin, oracle_mod, demo, small_synth, variant):
-    """-DLUMCU_ROLL -DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD (off by default) through the real kernels."""
+    """-DLUMCU_ROLL -DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD -DLUMCU_HASH_SHARE (off by default) through the real
+    kernels; 43 and 20 probes leave a ragged last batch, rays = 16 and 256 change the probes per batch."""
     O = oracle_mod
     check(emu_optin, O, demo, O.build_requests(demo["world"])[1000:1043], 5, variant)
     check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:20], 11, variant)
+    if variant == POOL:
+        check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:29], -3, variant, rays=16)
+        check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:5], 77, variant, rays=256)

@@ -1,16 +1,16 @@
 #!/bin/bash
-# First GPU call of the next round: build the opt-in variants (DESIGN.md 8, item 1) next to the default, check
+# First GPU call of the next round: build the opt-in variants (DESIGN.md 8, items 1 and 5) next to the default, check
 # each against the parity suite and time it on the C4 and demo worlds.
 #   here:          bash tools/next_round_sweep.sh build
 #   under gpurun:  bash tools/next_round_sweep.sh run      -> gpurun_out/next_round_sweep.log
 set -e
 cd "$(dirname "$0")/.."
-VARIANTS=("base:" "spec2wg:-DLUMCU_SPEC2_WG" "refahead:-DLUMCU_REFINE_AHEAD" "both:-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD" "roll:-DLUMCU_ROLL" "roll_refahead:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD" "nospec2:-DLUMCU_NO_SPEC2")
+VARIANTS=("base:" "spec2wg:-DLUMCU_SPEC2_WG" "refahead:-DLUMCU_REFINE_AHEAD" "both:-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD" "roll:-DLUMCU_ROLL" "roll10:-DLUMCU_ROLL -DLUMCU_MINB=10" "refahead10:-DLUMCU_REFINE_AHEAD -DLUMCU_MINB=10" "hashshare10:-DLUMCU_HASH_SHARE -DLUMCU_MINB=10" "all10:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD -DLUMCU_HASH_SHARE -DLUMCU_SPEC2_WG -DLUMCU_MINB=10" "roll_refahead:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD" "nospec2:-DLUMCU_NO_SPEC2")
 if [ "$1" = build ]; then
   for v in "${VARIANTS[@]}"; do
     n=${v%%:*}; f=${v#*:}
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false \
-         -Xcompiler -fPIC,-ffp-contract=off,-Wall -I include $f -shared -o lum_b200/exp_$n.so lum_b200/csrc/lumcu.cu
+         -Xcompiler -fPIC,-ffp-contract=off,-Wall -I include $f -shared -o lum_b200/exp_$n.so lum_b200/csrc/lumcu.cu 2>&1 | grep -v "minnctapersm will be ignored" || true
     echo "built lum_b200/exp_$n.so ($f)"
   done
   exit 0
