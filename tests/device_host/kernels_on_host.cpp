@@ -83,3 +83,35 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
     });
     return 0;
 }
+
+// The request-list builder as lumcu_build_requests launches it: count -> scan -> ordered scatter (-> specials).
+// out: int16 [cap][4]; returns the request count, *nbuilt = the z-sorted part (without the special tail).
+extern "C" long long kernels_on_host_build_requests(int wx, int wy, int wz, const int16_t *world, const int16_t *special,
+                                                    int nspecial, int16_t *out, long long cap, long long *nbuilt) {
+    const long long cells = (long long)wx * wy * wz;
+    const long long nblocks = (cells + BUILD_THREADS - 1) / BUILD_THREADS;
+    std::vector<uint8_t> flags((size_t)cells);
+    std::vector<uint32_t> counts((size_t)nblocks);
+    std::vector<unsigned long long> offsets((size_t)nblocks);
+    unsigned long long total = 0;
+    short4 *o = reinterpret_cast<short4 *>(out);
+    emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_count_kernel(world, wx, wy, wz, flags.data(), counts.data()); });
+    emu_launch(1, 1, 1024, [&] { build_scan_kernel(counts.data(), offsets.data(), nblocks, &total); });
+    emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_scatter_kernel(flags.data(), offsets.data(), wx, wy, wz, o, cap); });
+    *nbuilt = (long long)total;
+    if (nspecial > 0)
+        emu_launch(1, 1, 1024, [&] {
+            build_specials_kernel(flags.data(), wx, wy, wz, reinterpret_cast<const short4 *>(special), nspecial, o, &total, cap);
+        });
+    return (long long)total;
+}
+
+// shift_radiance as lumcu_shift launches it (tmp = copy of the field).
+extern "C" int kernels_on_host_shift(int wx, int wy, int wz, uint32_t *field, int dx, int dy, int dz) {
+    const long long cells = (long long)wx * wy * wz;
+    if ((dx == 0 && dy == 0 && dz == 0) || abs(dx) >= wx || abs(dy) >= wy || abs(dz) >= wz) return 0;
+    std::vector<uint32_t> tmp(field, field + cells);
+    const int t = 256;
+    emu_launch((unsigned)((cells + t - 1) / t), 1, t, [&] { shift_kernel(field, tmp.data(), wx, wy, wz, dx, dy, dz); });
+    return 0;
+}

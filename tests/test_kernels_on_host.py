@@ -147,3 +147,37 @@ def test_optin_variants_kernel_integration(emu_optin, oracle_mod, demo, small_sy
     if variant == POOL:
         check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:29], -3, variant, rays=16)
         check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:5], 77, variant, rays=256)
+
+
+def test_request_builder_kernels(emu, oracle_mod, demo):
+    """SURVEY a13 on the emulator: build_count / build_scan / build_scatter / build_specials against the oracle's list
+    (demo world: 2,689 requests in z,y,x order; specials appended in submission order unless already selected)."""
+    O = oracle_mod
+    emu.kernels_on_host_build_requests.restype = C.c_longlong
+    world = np.ascontiguousarray(demo["world"], np.int16)
+    wz, wy, wx = world.shape
+    p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    rng = np.random.default_rng(0)
+    specials = np.array([(int(rng.integers(0, wx)), int(rng.integers(0, wy)), int(rng.integers(0, wz)), 0) for _ in range(40)]
+                        + [(3, 3, 15, 0), (3, 3, 15, 0)], np.int16)          # duplicates among specials are kept
+    for sp in (None, specials):
+        nsp = 0 if sp is None else len(sp)
+        out = np.zeros((world.size + nsp, 4), np.int16)
+        nbuilt = C.c_longlong(0)
+        n = emu.kernels_on_host_build_requests(C.c_int(wx), C.c_int(wy), C.c_int(wz), p(world), p(sp), C.c_int(nsp),
+                                               p(out), C.c_longlong(len(out)), C.byref(nbuilt))
+        ref = O.build_requests(world, sp)
+        assert nbuilt.value == 2689
+        assert n == len(ref)
+        assert np.array_equal(out[:n], ref)
+
+
+@pytest.mark.parametrize("d", [(1, 0, 0), (0, -2, 1), (-3, 4, -1), (0, 0, 0), (48, 0, 0)])
+def test_shift_kernel(emu, oracle_mod, d):
+    O = oracle_mod
+    wx, wy, wz = 12, 10, 6
+    f = np.random.default_rng(1).integers(0, 2 ** 32, wx * wy * wz, dtype=np.uint64).astype(np.uint32)
+    ref = O.shift_field(f.copy(), (wx, wy, wz), *d)
+    got = f.copy()
+    emu.kernels_on_host_shift(C.c_int(wx), C.c_int(wy), C.c_int(wz), got.ctypes.data_as(C.c_void_p), *[C.c_int(v) for v in d])
+    assert np.array_equal(got, np.asarray(ref).reshape(-1))
