@@ -86,6 +86,8 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
 
 // The request-list builder as lumcu_build_requests launches it: count -> scan -> ordered scatter (-> specials).
 // out: int16 [cap][4]; returns the request count, *nbuilt = the z-sorted part (without the special tail).
+// (The two single-CTA kernels run with 256 instead of 1024 threads here -- they are written for any multiple of 32 --
+// to keep the emulator at 256 OS threads.)
 extern "C" long long kernels_on_host_build_requests(int wx, int wy, int wz, const int16_t *world, const int16_t *special,
                                                     int nspecial, int16_t *out, long long cap, long long *nbuilt) {
     const long long cells = (long long)wx * wy * wz;
@@ -96,11 +98,11 @@ extern "C" long long kernels_on_host_build_requests(int wx, int wy, int wz, cons
     unsigned long long total = 0;
     short4 *o = reinterpret_cast<short4 *>(out);
     emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_count_kernel(world, wx, wy, wz, flags.data(), counts.data()); });
-    emu_launch(1, 1, 1024, [&] { build_scan_kernel(counts.data(), offsets.data(), nblocks, &total); });
+    emu_launch(1, 1, 256, [&] { build_scan_kernel(counts.data(), offsets.data(), nblocks, &total); });
     emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_scatter_kernel(flags.data(), offsets.data(), wx, wy, wz, o, cap); });
     *nbuilt = (long long)total;
     if (nspecial > 0)
-        emu_launch(1, 1, 1024, [&] {
+        emu_launch(1, 1, 256, [&] {
             build_specials_kernel(flags.data(), wx, wy, wz, reinterpret_cast<const short4 *>(special), nspecial, o, &total, cap);
         });
     return (long long)total;
