@@ -181,3 +181,30 @@ def test_shift_kernel(emu, oracle_mod, d):
     got = f.copy()
     emu.kernels_on_host_shift(C.c_int(wx), C.c_int(wy), C.c_int(wz), got.ctypes.data_as(C.c_void_p), *[C.c_int(v) for v in d])
     assert np.array_equal(got, np.asarray(ref).reshape(-1))
+
+
+@pytest.mark.parametrize("defines", [(), ("LUMCU_ROLL", "LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD", "LUMCU_HASH_SHARE")],
+                         ids=["default", "optin"])
+def test_emulated_kernels_are_race_free_under_tsan(defines):
+    """Host-side racecheck: tests/device_host/tsan_main.cpp runs the emulated pooled and per-workgroup kernels (dense
+    random world: refill, parking, tail passes) under ThreadSanitizer.  Every CUDA thread is an OS thread and every
+    barrier / warp collective a real synchronisation, so a missing __syncthreads / __syncwarp in the kernels is a
+    data race TSAN reports (removing the barrier after pass 0 of the march yields 31 reports)."""
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    src = os.path.join(HERE, "device_host", "tsan_main.cpp")
+    exe = os.path.join(HERE, "_build", "tsan_" + ("optin" if defines else "default"))
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    r = subprocess.run(["g++", "-fsanitize=thread", "-O1", "-g", "-std=c++17", "-pthread", "-ffp-contract=off",
+                        "-fno-fast-math", "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines], "-I", CUDA_INC,
+                        "-o", exe, src], capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in r.stderr.lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert r.returncode == 0, r.stderr
+    run_ = subprocess.run([exe], capture_output=True, text=True, timeout=600,
+                          env=dict(os.environ, TSAN_OPTIONS="exitcode=66"))
+    if "FATAL: ThreadSanitizer" in run_.stderr:          # e.g. an unsupported memory layout inside a sandbox
+        pytest.skip("ThreadSanitizer cannot run here: " + run_.stderr.splitlines()[0])
+    assert "WARNING: ThreadSanitizer" not in run_.stderr, run_.stderr[:4000]
+    assert run_.returncode == 0, run_.stderr[:2000]
+    assert run_.stdout.count("S=") == 4
