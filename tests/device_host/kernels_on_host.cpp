@@ -117,3 +117,23 @@ extern "C" int kernels_on_host_shift(int wx, int wy, int wz, uint32_t *field, in
     emu_launch((unsigned)((cells + t - 1) / t), 1, t, [&] { shift_kernel(field, tmp.data(), wx, wy, wz, dx, dy, dz); });
     return 0;
 }
+
+// exec_copies as lumcu_copy_bricks launches it: one CTA of 256 threads per (src, dst) pair, 16 bytes per thread.
+extern "C" int kernels_on_host_copy_bricks(uint8_t *bricks, int capacity, const int32_t *src, const int32_t *dst, int n) {
+    std::vector<int2> pairs((size_t)std::max(n, 1));
+    for (int i = 0; i < n; i++) { pairs[i].x = src[i]; pairs[i].y = dst[i]; }
+    if (n > 0) emu_launch((unsigned)n, 1, 256, [&] { copy_bricks_kernel(bricks, pairs.data(), n, capacity); });
+    return 0;
+}
+
+// lumcu_slab_range: first workgroup with z >= z_begin / z >= z_end in the z-sorted part of the request list.
+extern "C" int kernels_on_host_slab_range(const int16_t *requests, long long nwg_sorted, int size, int shift,
+                                          int z_begin, int z_end, long long *out2) {
+    out2[0] = nwg_sorted; out2[1] = nwg_sorted;
+    const int t = 256;
+    if (nwg_sorted > 0)
+        emu_launch((unsigned)((nwg_sorted + t - 1) / t), 1, t, [&] {
+            slab_bound_kernel(reinterpret_cast<const short4 *>(requests), nwg_sorted, size, shift, z_begin, z_end, out2);
+        });
+    return 0;
+}

@@ -208,3 +208,33 @@ def test_emulated_kernels_are_race_free_under_tsan(defines):
     assert "WARNING: ThreadSanitizer" not in run_.stderr, run_.stderr[:4000]
     assert run_.returncode == 0, run_.stderr[:2000]
     assert run_.stdout.count("S=") == 4
+
+
+def test_copy_bricks_kernel(emu, oracle_mod, demo):
+    """exec_copies: static bricks copied into dynamic ones, source 0 zeroes the destination."""
+    O = oracle_mod
+    rng = np.random.default_rng(0)
+    bricks = np.concatenate([demo["bricks"], rng.integers(0, 256, (49, 16, 16, 16)).astype(np.uint8)])   # stale dynamic bricks
+    src = rng.integers(0, 15, 40).astype(np.int32)
+    dst = np.arange(20, 60, dtype=np.int32)
+    ref = bricks.copy()
+    O.copy_bricks(ref, src, dst)
+    got = np.ascontiguousarray(bricks.copy())
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emu.kernels_on_host_copy_bricks(p(got), C.c_int(len(got)), p(src), p(dst), C.c_int(len(src))) == 0
+    assert np.array_equal(got, ref)
+    assert (got[dst[src == 0]] == 0).all()
+
+
+def test_slab_bound_kernel(emu, oracle_mod, demo):
+    """The z-slab boundaries of the multi-GPU slab sharding (lumcu_slab_range) against a binary search."""
+    O = oracle_mod
+    req = np.ascontiguousarray(O.build_requests(demo["world"]), np.int16)
+    z = req[:, 2].astype(np.int64)
+    out = np.zeros(2, np.int64)
+    for size, shift in ((1, 0), (3, 1)):
+        zs = z[shift::size][: len(req) // size]
+        for zb, ze in ((0, 16), (4, 8), (8, 12), (15, 16), (-5, 3), (16, 40)):
+            emu.kernels_on_host_slab_range(req.ctypes.data_as(C.c_void_p), C.c_longlong(len(zs)), C.c_int(size), C.c_int(shift),
+                                           C.c_int(zb), C.c_int(ze), out.ctypes.data_as(C.c_void_p))
+            assert (int(out[0]), int(out[1])) == (int(np.searchsorted(zs, zb, "left")), int(np.searchsorted(zs, ze, "left")))
