@@ -20,14 +20,14 @@ static void launch_wg(const SceneView &s, const UpdateArgs &a, long long nwg) {
     emu_launch((unsigned)nwg, 1, R, [&] { radiance_update_wg_kernel<R, true>(s, a); });
 }
 
-// variant: 0 = one workgroup per CTA, 1 = pooled.  il_rank / il_n: interleaved shard (il_n = 1: everything).
-extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
-                                      const int16_t *world, const uint8_t *bricks, const float *materials,
-                                      const uint32_t *field_old, uint32_t *field_new,
-                                      const int16_t *requests, long long nreq, int time_seed, int size, int shift,
-                                      const float *table, const float *sun3, int variant, int il_rank, int il_n,
-                                      float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals) {
-    if (size < 1 || shift < 0 || shift >= size || il_n < 1 || il_rank < 0 || il_rank >= il_n) return -1;
+// Trace workgroups [0, nreq/size) of shard il into staged[] (validate_world_kernel first, like ensure_validated()).
+// variant: 0 = one workgroup per CTA, 1 = pooled.  Returns the workgroups traced, < 0 on bad arguments.
+static long long trace_on_host(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
+                               const int16_t *world, const uint8_t *bricks, const float *materials, const uint32_t *field_old,
+                               const int16_t *requests, long long nreq, int time_seed, int size, int shift,
+                               const float *table, const float *sun3, int variant, Interleave il, uint32_t *staged,
+                               float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals) {
+    if (size < 1 || shift < 0 || shift >= size || il.n < 1 || il.rank < 0 || il.rank >= il.n || il.chunk < 1) return -1;
     std::vector<float4> mat4(256);
     for (int i = 0; i < 256; i++) mat4[i] = make_float4(materials[6 * i], materials[6 * i + 1], materials[6 * i + 2], materials[6 * i + 4]);
     const long long cells = (long long)wx * wy * wz;
@@ -35,15 +35,13 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
     emu_launch(2, 1, 64, [&] { validate_world_kernel(world, cells, capacity, &flags); });
     const SceneView s{world, bricks, materials, mat4.data(), field_old, wx, wy, wz, capacity, brick0_empty, &flags};
     const long long nwg_all = nreq / size;
-    std::vector<uint32_t> staged((size_t)std::max<long long>(nwg_all, 1));
     UpdateArgs a{};
     a.requests = reinterpret_cast<const short4 *>(requests);
     a.dir_table = table;
-    a.staged = staged.data();
+    a.staged = staged;
     a.dbg_pre_blend = pre_blend; a.dbg_samples = ray_samples; a.dbg_hits = ray_hits; a.dbg_totals = totals;
     a.wg_begin = 0; a.wg_end = nwg_all;
-    constexpr int IL_CHUNK = 3072;
-    a.il_chunk = IL_CHUNK; a.il_rank = il_rank; a.il_n = il_n;
+    a.il_chunk = il.chunk; a.il_rank = il.rank; a.il_n = il.n;
     a.time_seed = time_seed; a.size = size; a.shift = shift;
     a.z_begin = -32768; a.z_end = 32768;
     a.reactiveness = reactiveness;
@@ -51,11 +49,10 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
     totals[0] = totals[1] = 0;
     // workgroups this launch traces (lumcu.cu: il_count)
     long long nwg = nwg_all;
-    if (il_n > 1) {
-        const long long full = nwg_all / IL_CHUNK, rem = nwg_all % IL_CHUNK;
-        nwg = (full / il_n) * IL_CHUNK + ((full % il_n) > il_rank ? IL_CHUNK : 0) + ((full % il_n) == il_rank ? rem : 0);
+    if (il.n > 1) {
+        const long long full = nwg_all / il.chunk, rem = nwg_all % il.chunk;
+        nwg = (full / il.n) * il.chunk + ((full % il.n) > il.rank ? il.chunk : 0) + ((full % il.n) == il.rank ? rem : 0);
     }
-    for (long long i = 0; i < cells; i++) field_new[i] = field_old[i];
     if (nwg <= 0) return 0;
     if (variant == 1) {
         switch (R) {
@@ -76,11 +73,65 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
             default: return -1;
         }
     }
+    return nwg;
+}
+
+constexpr int IL_CHUNK = 3072;     // lumcu.cu
+
+// One update on one device, as lumcu_update launches it: trace, then commit_kernel.
+extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
+                                      const int16_t *world, const uint8_t *bricks, const float *materials,
+                                      const uint32_t *field_old, uint32_t *field_new,
+                                      const int16_t *requests, long long nreq, int time_seed, int size, int shift,
+                                      const float *table, const float *sun3, int variant, int il_rank, int il_n,
+                                      float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals) {
+    const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? nreq / size : 0;
+    std::vector<uint32_t> staged((size_t)std::max<long long>(nwg_all, 1));
     const Interleave il{IL_CHUNK, il_rank, il_n};
+    const long long nwg = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials, field_old,
+                                        requests, nreq, time_seed, size, shift, table, sun3, variant, il, staged.data(),
+                                        pre_blend, ray_samples, ray_hits, totals);
+    if (nwg < 0) return -1;
+    for (long long i = 0; i < cells; i++) field_new[i] = field_old[i];
+    if (nwg == 0) return 0;
     const int ct = 64;
     emu_launch((unsigned)((nwg + ct - 1) / ct), 1, ct, [&] {
-        commit_kernel(field_new, staged.data(), a.requests, 0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, il);
+        commit_kernel(field_new, staged.data(), reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, il);
     });
+    return 0;
+}
+
+// One frame on `nranks` devices as lumcu_update_shard_exchange runs it: every rank traces its interleaved shard reading
+// its own replica of the field (all equal), then -- after what is peer_barrier_kernel(0) on the device -- stores its
+// texels into EVERY replica with commit_peers_kernel.  replicas: uint32 [nranks][cells], in = old field, out = new field.
+// il_chunk must be a multiple of the pooled kernel's probes per CTA (lumcu.cu uses 3072; small here so that a small
+// dispatch is really dealt to several ranks).
+extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
+                                              const int16_t *world, const uint8_t *bricks, const float *materials,
+                                              uint32_t *replicas, int nranks, int il_chunk,
+                                              const int16_t *requests, long long nreq, int time_seed, int size, int shift,
+                                              const float *table, const float *sun3, int variant) {
+    if (nranks < 1 || nranks > MAX_PEERS) return -1;
+    const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? nreq / size : 0;
+    std::vector<std::vector<uint32_t>> staged((size_t)nranks, std::vector<uint32_t>((size_t)std::max<long long>(nwg_all, 1)));
+    std::vector<long long> traced((size_t)nranks);
+    unsigned long long tot[2];
+    for (int r = 0; r < nranks; r++) {
+        traced[r] = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials,
+                                  replicas + (size_t)r * cells, requests, nreq, time_seed, size, shift, table, sun3, variant,
+                                  Interleave{il_chunk, r, nranks}, staged[r].data(), nullptr, nullptr, nullptr, tot);
+        if (traced[r] < 0) return -1;
+    }
+    PeerFields pf{};
+    pf.n = nranks;
+    for (int p = 0; p < nranks; p++) pf.f[p] = replicas + (size_t)p * cells;
+    const int ct = 64;
+    for (int r = 0; r < nranks; r++)
+        if (traced[r] > 0)
+            emu_launch((unsigned)((traced[r] + ct - 1) / ct), 1, ct, [&] {
+                commit_peers_kernel(pf, staged[r].data(), reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift,
+                                    wx, wy, wz, -32768, 32768, Interleave{il_chunk, r, nranks});
+            });
     return 0;
 }
 

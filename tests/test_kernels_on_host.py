@@ -238,3 +238,30 @@ def test_slab_bound_kernel(emu, oracle_mod, demo):
             emu.kernels_on_host_slab_range(req.ctypes.data_as(C.c_void_p), C.c_longlong(len(zs)), C.c_int(size), C.c_int(shift),
                                            C.c_int(zb), C.c_int(ze), out.ctypes.data_as(C.c_void_p))
             assert (int(out[0]), int(out[1])) == (int(np.searchsorted(zs, zb, "left")), int(np.searchsorted(zs, ze, "left")))
+
+
+@pytest.mark.parametrize("nranks,variant", [(2, POOL), (3, POOL), (2, WG)])
+def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant):
+    """SURVEY 8e on the emulator: the dispatch dealt to `nranks` ranks in interleaved chunks (il_map in the kernels), every
+    rank's texels stored into every replica by commit_peers_kernel -- all replicas equal the single-device field."""
+    O = oracle_mod
+    sc = scene_of(O, small_synth)
+    req = np.ascontiguousarray(O.build_requests(small_synth["world"])[::53][:45], np.int16)      # 45 probes, chunks of 12
+    f0 = np.random.default_rng(8).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 4)["field"]
+    world = np.ascontiguousarray(small_synth["world"], np.int16)
+    bricks = np.ascontiguousarray(small_synth["bricks"], np.uint8)
+    mats = np.ascontiguousarray(small_synth["materials"], np.float32)
+    wz, wy, wx = world.shape
+    replicas = np.ascontiguousarray(np.tile(f0, (nranks, 1)))
+    table = np.ascontiguousarray(O.direction_table(64), np.float32)
+    sun = np.ascontiguousarray(O.sun_dir(), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.kernels_on_host_update_sharded.restype = C.c_int
+    rc = emu.kernels_on_host_update_sharded(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]), C.c_int(1),
+                                            C.c_int(64), C.c_float(0.01), p(world), p(bricks), p(mats), p(replicas),
+                                            C.c_int(nranks), C.c_int(12), p(req), C.c_longlong(len(req)), C.c_int(4),
+                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant))
+    assert rc == 0
+    for r in range(nranks):
+        assert np.array_equal(replicas[r], ref), r
