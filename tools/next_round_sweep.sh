@@ -5,7 +5,7 @@
 #   under gpurun:  bash tools/next_round_sweep.sh run      -> gpurun_out/next_round_sweep.log
 set -e
 cd "$(dirname "$0")/.."
-VARIANTS=("base:" "spec2wg:-DLUMCU_SPEC2_WG" "refahead:-DLUMCU_REFINE_AHEAD" "both:-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD" "roll:-DLUMCU_ROLL" "roll10:-DLUMCU_ROLL -DLUMCU_MINB=10" "refahead10:-DLUMCU_REFINE_AHEAD -DLUMCU_MINB=10" "hashshare10:-DLUMCU_HASH_SHARE -DLUMCU_MINB=10" "all10:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD -DLUMCU_HASH_SHARE -DLUMCU_SPEC2_WG -DLUMCU_MINB=10" "roll_refahead:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD" "nospec2:-DLUMCU_NO_SPEC2")
+VARIANTS=("base:" "base10:-DLUMCU_MINB=10" "spec2wg:-DLUMCU_SPEC2_WG" "refahead:-DLUMCU_REFINE_AHEAD" "both:-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD" "roll:-DLUMCU_ROLL" "roll10:-DLUMCU_ROLL -DLUMCU_MINB=10" "refahead10:-DLUMCU_REFINE_AHEAD -DLUMCU_MINB=10" "hashshare10:-DLUMCU_HASH_SHARE -DLUMCU_MINB=10" "all10:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD -DLUMCU_HASH_SHARE -DLUMCU_SPEC2_WG -DLUMCU_MINB=10" "roll_refahead:-DLUMCU_ROLL -DLUMCU_REFINE_AHEAD" "nospec2:-DLUMCU_NO_SPEC2")
 if [ "$1" = build ]; then
   for v in "${VARIANTS[@]}"; do
     n=${v%%:*}; f=${v#*:}
