@@ -25,6 +25,8 @@ OUT = os.path.join(HERE, "_build", "libkernels_on_host.so")
 
 POOL, WG = 1, 0
 
+pytestmark = pytest.mark.timeout(900)      # pytest-timeout: a deadlocked emulator must fail, not hang the suite
+
 
 def build(out, defines=()):
     if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
