@@ -115,6 +115,9 @@ void lum_b200_set_radiance_shift(LumRenderer instance, int dx, int dy, int dz);
  * = keep magic_size fixed (magic_size 1 = every probe every frame). */
 void lum_b200_set_radiance_controller(LumRenderer instance, bool enabled, int magic_size);
 int lum_b200_get_magic_size(const LumRenderer instance);
+/* ms >= 0: the controller sees this as the measured time of every dispatch (timeTakenByRadiance,
+ * internal_render.cpp:2173) instead of the GPU timestamps; ms < 0: measure (default). */
+void lum_b200_set_radiance_time_override(LumRenderer instance, float ms);
 long long lum_b200_get_request_count(const LumRenderer instance);
 int lum_b200_get_frame_index(const LumRenderer instance);
 /* Radiance field, A2B10G10R10 words, index x + X*(y + Y*z): world_size cells. */

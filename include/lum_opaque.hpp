@@ -88,6 +88,8 @@ public:
     float timeTakenByRadiance = 0.0f;                // ms, measured on the previous frame's dispatch
     int magicSize = 2;
     bool radianceControllerEnabled = true;           // false: magicSize stays as set (tests, benchmarks)
+    float radianceTimeOverride = -1.0f;              // >= 0: what end_frame reports as the dispatch time instead of the
+                                                     // measured one (makes the controller's trajectory reproducible)
 
     // ---- B200 stage ----
     LumcuCtx* stage = nullptr;

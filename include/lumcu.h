@@ -179,8 +179,12 @@ int lumcu_direction_table(LumcuCtx *ctx, float *out);
 /* Instrumentation (parity tests + roofline numerator).  flags = LUMCU_DEBUG_* bits; while
  * non-zero, lumcu_update runs the instrumented kernel variant and fills the debug buffers. */
 int lumcu_set_debug(LumcuCtx *ctx, int32_t flags);
-/* pre_blend: nwg*3 floats; ray_samples: nwg*R uint32; ray_hits: nwg*R uint8; totals: S,H,N of
- * the last instrumented update.  Any pointer may be NULL. */
+/* Extent of what the last instrumented update left in the debug buffers: *nwg workgroups starting at workgroup
+ * *wg_begin of the dispatch (for a shard update: the whole range, of which only the shard's entries were written).
+ * lumcu_download_debug copies exactly this many entries: size the output buffers from it. */
+int lumcu_debug_extent(LumcuCtx *ctx, int64_t *nwg, int64_t *wg_begin);
+/* pre_blend: nwg*3 floats; ray_samples: nwg*R uint32; ray_hits: nwg*R uint8 (nwg from lumcu_debug_extent); totals:
+ * S,H,N of the last instrumented update.  Any pointer may be NULL. */
 int lumcu_download_debug(LumcuCtx *ctx, float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits,
                          uint64_t totals[3]);
 

@@ -72,6 +72,7 @@ SYMBOLS = {
     "lumcu_download_field": (C.c_int, [_P, _P]),
     "lumcu_direction_table": (C.c_int, [_P, _P]),
     "lumcu_set_debug": (C.c_int, [_P, C.c_int32]),
+    "lumcu_debug_extent": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "lumcu_download_debug": (C.c_int, [_P, _P, _P, _P, _P]),
     "lumcu_debug_unpack_table": (C.c_int, [_P, _P]),
     "lumcu_wait_idle": (C.c_int, [_P]),
@@ -295,7 +296,16 @@ class RadianceStage:
     def set_debug(self, flags):
         self._ck(self.lib.lumcu_set_debug(self.ctx, int(flags)))
 
-    def download_debug(self, nwg, pre_blend=True, rays=False):
+    def debug_extent(self):
+        n, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.lumcu_debug_extent(self.ctx, C.byref(n), C.byref(b)))
+        return int(n.value), int(b.value)
+
+    def download_debug(self, nwg=None, pre_blend=True, rays=False):
+        """Debug buffers of the last instrumented update.  The library copies debug_extent()[0] workgroups, so the
+        buffers are sized from that (`nwg` can only make them larger)."""
+        have = self.debug_extent()[0]
+        nwg = have if nwg is None else max(int(nwg), have)      # never smaller than what the library copies
         pre = np.zeros((nwg, 3), np.float32) if pre_blend else None
         rs = np.zeros(nwg * self.rays, np.uint32) if rays else None
         rh = np.zeros(nwg * self.rays, np.uint8) if rays else None

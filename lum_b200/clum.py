@@ -71,6 +71,7 @@ SYMBOLS = {
     "lum_b200_set_radiance_shift": (None, [_P, C.c_int, C.c_int, C.c_int]),
     "lum_b200_set_radiance_controller": (None, [_P, C.c_bool, C.c_int]),
     "lum_b200_get_magic_size": (C.c_int, [_P]),
+    "lum_b200_set_radiance_time_override": (None, [_P, C.c_float]),
     "lum_b200_get_request_count": (C.c_longlong, [_P]),
     "lum_b200_get_frame_index": (C.c_int, [_P]),
     "lum_b200_download_radiance_field": (None, [_P, _P]),
@@ -218,6 +219,9 @@ class Renderer:
 
     def set_radiance_controller(self, enabled, magic_size=0):
         self.lib.lum_b200_set_radiance_controller(self.h, enabled, magic_size)
+
+    def set_radiance_time_override(self, ms):
+        self.lib.lum_b200_set_radiance_time_override(self.h, float(ms))
 
     def magic_size(self):
         return self.lib.lum_b200_get_magic_size(self.h)

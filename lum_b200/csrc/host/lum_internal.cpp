@@ -306,7 +306,8 @@ void LumInternalRenderer::end_frame() {                                  // :208
     float ms = timeTakenByRadiance;
     // the pair of timestamps around the dispatch (:1205-1207).  Reading it waits for the dispatch, so
     // it is skipped when nothing consumes it (controller off and profiling off).
-    if (radianceControllerEnabled || lumal.settings.profile) check(lumcu_last_update_ms(stage, &ms), "lumcu_last_update_ms");
+    if (radianceTimeOverride >= 0.0f) ms = radianceTimeOverride;
+    else if (radianceControllerEnabled || lumal.settings.profile) check(lumcu_last_update_ms(stage, &ms), "lumcu_last_update_ms");
     timeTakenByRadiance = ms;                                            // :2173
     // timestamps 0 and 1 bracket the radiance dispatch (:1205-1207)
     lumal.currentTimestamp = 0;

@@ -72,6 +72,9 @@ bool read_scene(const uint8_t* data, size_t size, Scene& out, std::string& err) 
         if (cid == id4('M', 'A', 'I', 'N')) continue;                       // children follow inline
         if (cid == id4('S', 'I', 'Z', 'E')) {
             if (!rd.u32(sx) || !rd.u32(sy) || !rd.u32(sz) || !sx || !sy || !sz) { err = "bad SIZE chunk"; return false; }
+            // XYZI coordinates are bytes: the format cannot address more than 256 voxels per axis.  Anything larger is
+            // a corrupt or hostile file (the product of three unchecked 32-bit sizes can wrap the allocation below).
+            if (sx > 256 || sy > 256 || sz > 256) { err = "SIZE chunk exceeds the .vox limit of 256 per axis"; return false; }
         } else if (cid == id4('X', 'Y', 'Z', 'I')) {
             uint32_t count = 0;
             if (!sx || !rd.u32(count)) { err = "XYZI before SIZE"; return false; }
@@ -122,7 +125,9 @@ bool read_scene(const uint8_t* data, size_t size, Scene& out, std::string& err) 
 
     if (have_imap) {
         // imap[display index] = stored index.  Palette, materials and voxel indices go to display order.
-        uint8_t inv[256];
+        // (an IMAP that is not a permutation leaves entries of the inverse unnamed -- indeterminate in the reference
+        // decoder, ogt_vox.hpp:2016-2019; zero here)
+        uint8_t inv[256] = {0};
         for (int i = 0; i < 256; i++) inv[imap[i]] = (uint8_t)i;
         uint8_t oldp[256][4];
         memcpy(oldp, out.palette, sizeof oldp);

@@ -99,6 +99,7 @@ struct LumcuCtx {
     long long nreq = 0;          // current request count
     long long nsorted = 0;       // leading requests known to be z-sorted
     bool have_world = false, have_bricks = false, have_materials = false;
+    int sm_count = 148;          // cudaDevAttrMultiProcessorCount (grid sizing of the grid-stride kernels)
     int pool_threads = 128;      // tuning knobs (env LUMCU_POOL_THREADS / LUMCU_CARVEOUT, read at create)
     int carveout = -1;
     int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
@@ -184,6 +185,9 @@ void host_direction_table(int n, std::vector<float> &out) {
     }
 }
 
+// Interleaved sharding (UpdateArgs::il_*): chunk is a multiple of every pooled kernel's probes-per-CTA.
+constexpr int IL_CHUNK = 3072;
+
 // production path: pooled kernel (no z filter); one CTA per RPT*threads rays
 #ifndef LUMCU_RPT
 #define LUMCU_RPT 3           // rays per thread of the reference-shaped (R = 64) production kernel: 384 rays = 6 probes
@@ -192,6 +196,7 @@ void host_direction_table(int n, std::vector<float> &out) {
 template <int R, int T, int RPT, bool DEBUG>
 int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
     constexpr int ppc = RPT * T / R;
+    static_assert(ppc >= 1 && IL_CHUNK % ppc == 0, "an interleaved chunk must hold whole CTA batches (il_map)");
     auto k = radiance_update_pool_kernel<R, T, RPT, DEBUG>;
     if (c->carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout);
     dim3 grid((unsigned)((nwg + ppc - 1) / ppc));
@@ -208,12 +213,8 @@ int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, lo
     switch (c->R) {
         case 16: return launch_pool_one<16, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         case 32: return launch_pool_one<32, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
-#ifdef LUMCU_T64
-        case 64: return launch_pool_one<64, 64, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
-#else
         case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg)
                                                : launch_pool_one<64, 256, 4, DEBUG>(c, sv, a, nwg);
-#endif
         case 128: return launch_pool_one<128, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         case 256: return launch_pool_one<256, 256, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);
@@ -254,7 +255,7 @@ int ensure_validated(LumcuCtx *c) {
     if (c->world_dirty || c->world_shared) {
         CU(cudaMemsetAsync(c->d_scene_flags, 0, sizeof(uint32_t), c->stream));
         const int vt = 256;
-        const long long vb = std::min<long long>((c->cells + vt - 1) / vt, 148 * 8);
+        const long long vb = std::min<long long>((c->cells + vt - 1) / vt, (long long)c->sm_count * 8);
         validate_world_kernel<<<(unsigned)vb, vt, 0, c->stream>>>(c->d_world, c->cells, c->desc.palette_capacity, c->d_scene_flags);
         c->launches++;
         CU(cudaGetLastError());
@@ -265,11 +266,10 @@ int ensure_validated(LumcuCtx *c) {
 
 SceneView scene_view(LumcuCtx *c) {
     return SceneView{c->d_world, c->d_bricks, c->d_materials, c->d_mat4, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
-                     c->brick0_empty ? 1 : 0, c->d_scene_flags};
+                     c->brick0_empty ? 1 : 0, c->d_scene_flags
+    };
 }
 
-// Interleaved sharding (UpdateArgs::il_*): chunk is a multiple of every pooled kernel's probes-per-CTA.
-constexpr int IL_CHUNK = 3072;
 // number of workgroups of [0, total) that shard `il` owns
 long long il_count(long long total, const Interleave &il) {
     if (il.n <= 1) return total;
@@ -277,8 +277,22 @@ long long il_count(long long total, const Interleave &il) {
     return (full / il.n) * il.chunk + ((full % il.n) > il.rank ? il.chunk : 0) + ((full % il.n) == il.rank ? rem : 0);
 }
 
+int commit_local(LumcuCtx *c, int size, int shift, long long wg_begin, long long wg_end, int z_begin, int z_end,
+                 Interleave il = Interleave{IL_CHUNK, 0, 1}) {
+    const long long nwg = il_count(wg_end - wg_begin, il);
+    if (nwg <= 0) return 0;
+    const int ct = 256;
+    commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
+        c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// second_pass: this launch continues a frame another do_update() started (the special tail of a slab update): the
+// instrumented totals keep accumulating and the debug range stays the first pass's.
 int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begin, long long wg_end,
-              int z_begin, int z_end, bool commit = true, Interleave il = Interleave{IL_CHUNK, 0, 1}) {
+              int z_begin, int z_end, bool commit = true, Interleave il = Interleave{IL_CHUNK, 0, 1}, bool second_pass = false) {
     if (!c->have_world || !c->have_bricks || !c->have_materials)
         return fail(LUMCU_E_STATE, "lumcu_update before world/bricks/materials were uploaded");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
@@ -310,22 +324,21 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             a.dbg_samples = (c->debug_flags & LUMCU_DEBUG_RAYS) ? c->d_ray_samples : nullptr;
             a.dbg_hits = (c->debug_flags & LUMCU_DEBUG_RAYS) ? c->d_ray_hits : nullptr;
             a.dbg_totals = c->d_totals;
-            CU(cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
+            if (!second_pass) CU(cudaMemsetAsync(c->d_totals, 0, 2 * sizeof(unsigned long long), c->stream));
             if (int rc = (use_pool ? launch_update_pool<true>(c, sv, a, nwg) : launch_update_R<true>(c, sv, a, nwg))) return rc;
-            c->dbg_traced = nwg;
-            c->dbg_nwg = il.n > 1 ? wg_end - wg_begin : nwg; c->dbg_wg_begin = wg_begin;   // (a shard leaves the other ranks' entries untouched)
+            if (second_pass) {
+                c->dbg_traced += nwg;
+            } else {
+                c->dbg_traced = nwg;
+                c->dbg_nwg = il.n > 1 ? wg_end - wg_begin : nwg; c->dbg_wg_begin = wg_begin;   // (a shard leaves the other ranks' entries untouched)
+            }
         } else {
             if (c->profiling) CU(cudaEventRecord(c->ev_k0, c->stream));
             if (int rc = (use_pool ? launch_update_pool<false>(c, sv, a, nwg) : launch_update_R<false>(c, sv, a, nwg))) return rc;
             if (c->profiling) { CU(cudaEventRecord(c->ev_k1, c->stream)); c->ktimed = true; }
         }
-        if (commit) {
-            const int ct = 256;
-            commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
-                c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il);
-            c->launches++;
-            CU(cudaGetLastError());
-        }
+        if (commit)
+            if (int rc = commit_local(c, size, shift, wg_begin, wg_end, z_begin, z_end, il)) return rc;
     }
     return 0;
 }
@@ -386,6 +399,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     auto bail = [&](int rc) { lumcu_destroy(c); return rc; };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(LUMCU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
     CUB(cudaSetDevice(d->device));
+    CUB(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, d->device));
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
@@ -548,6 +562,15 @@ int lumcu_copy_bricks(LumcuCtx *c, const int32_t *src, const int32_t *dst, int32
     for (int i = 0; i < n; i++)
         if (src[i] < 0 || src[i] >= c->desc.palette_capacity || dst[i] < 0 || dst[i] >= c->desc.palette_capacity)
             return fail(LUMCU_E_ARG, "brick copy %d: %d -> %d outside palette capacity %d", i, src[i], dst[i], c->desc.palette_capacity);
+    {   // the copies run concurrently (one CTA per pair): a destination may be neither a source nor written twice
+        std::vector<uint8_t> role((size_t)c->desc.palette_capacity, 0);      // 1 = source, 2 = destination
+        for (int i = 0; i < n; i++) role[src[i]] |= 1;
+        for (int i = 0; i < n; i++) {
+            if (role[dst[i]] & 1) return fail(LUMCU_E_ARG, "brick copy %d: destination %d is also a source", i, dst[i]);
+            if (role[dst[i]] & 2) return fail(LUMCU_E_ARG, "brick copy %d: destination %d appears twice", i, dst[i]);
+            role[dst[i]] |= 2;
+        }
+    }
     if (c->pairs_cap < n) {
         cudaFree(c->d_pairs); c->d_pairs = nullptr; c->pairs_cap = 0;
         long long cap = std::max<long long>(n, 256);
@@ -714,6 +737,10 @@ int lumcu_slab_range(LumcuCtx *c, int32_t size, int32_t shift, int32_t z_begin, 
     if (int rc = use(c)) return rc;
     if (size < 1 || shift < 0 || shift >= size || !wg_begin || !wg_end || z_begin > z_end)
         return fail(LUMCU_E_ARG, "bad slab arguments");
+    // request coordinates are int16: anything outside means "unbounded" (slab_bound_kernel's predecessor of the
+    // first workgroup is z = -32768, which must compare below every bound that can select something)
+    z_begin = std::min(std::max(z_begin, -32767), 32768);
+    z_end = std::min(std::max(z_end, -32767), 32768);
     if (c->slab_key_version == c->req_version && c->slab_key[0] == size && c->slab_key[1] == shift &&
         c->slab_key[2] == z_begin && c->slab_key[3] == z_end) {
         *wg_begin = c->slab_val[0]; *wg_end = c->slab_val[1];
@@ -745,9 +772,14 @@ int lumcu_update_slab(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shif
     if (int rc = lumcu_slab_range(c, size, shift, z_begin, z_end, &b, &e)) return rc;
     const long long nwg_all = c->nreq / size, tail = sorted_workgroups(c, size, shift);
     CU(cudaEventRecord(c->ev_begin, c->stream));
-    if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768)) return rc;
+    // Jacobi: both passes trace against the field as it was before the frame (the tail's rays may land in texels the
+    // sorted range is about to replace), so nothing is committed until both have run.
+    if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768, false)) return rc;
     if (tail < nwg_all)   // unsorted tail (specials): every rank scans it, keeps its slab's probes
-        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end)) return rc;
+        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false, Interleave{IL_CHUNK, 0, 1}, true)) return rc;
+    if (int rc = commit_local(c, size, shift, b, e, -32768, 32768)) return rc;
+    if (tail < nwg_all)
+        if (int rc = commit_local(c, size, shift, tail, nwg_all, z_begin, z_end)) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;
@@ -857,7 +889,7 @@ int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int
     CU(cudaEventRecord(c->ev_begin, c->stream));
     if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768, false)) return rc;
     if (tail < nwg_all)
-        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false)) return rc;
+        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false, Interleave{IL_CHUNK, 0, 1}, true)) return rc;
     if (int rc = peer_barrier(c, 0)) return rc;             // every rank has finished reading its field
     if (int rc = commit_to_peers(c, size, shift, b, e, -32768, 32768)) return rc;
     if (tail < nwg_all)
@@ -904,6 +936,13 @@ int lumcu_set_debug(LumcuCtx *c, int32_t flags) {
     if (int rc = use(c)) return rc;
     c->debug_flags = flags & (LUMCU_DEBUG_PRE_BLEND | LUMCU_DEBUG_RAYS);
     if (flags & ~(LUMCU_DEBUG_PRE_BLEND | LUMCU_DEBUG_RAYS)) return fail(LUMCU_E_ARG, "unknown debug flags 0x%x", flags);
+    return 0;
+}
+
+int lumcu_debug_extent(LumcuCtx *c, int64_t *nwg, int64_t *wg_begin) {
+    if (!c || !nwg) return fail(LUMCU_E_ARG, "null argument");
+    *nwg = c->dbg_nwg;
+    if (wg_begin) *wg_begin = c->dbg_wg_begin;
     return 0;
 }
 

@@ -246,8 +246,7 @@ __device__ __forceinline__ bool march_step_fast(const SceneView &s, const uint3 
     return hit || out || !(t < 128.0f);
 }
 
-// ---- two iterations at once, the second one's block-id fetch issued early (the pooled kernel's loop body;
-// -DLUMCU_NO_SPEC2 builds the two separate steps instead) ---------------------------------------------------
+// ---- two iterations at once, the second one's block-id fetch issued early (the loop body of every fast march) ----
 // A step is two dependent fetches (block id, then voxel), so two steps are four fetch latencies in a row.  But the
 // position of step B depends on step A's block id only (the empty-cell skip), not on A's voxel: B's block id can be
 // requested while A's voxel is still in flight -- id_A -> (voxel_A | id_B) -> voxel_B, three latencies instead of
@@ -299,78 +298,6 @@ __device__ __forceinline__ bool march_two_steps_fast(const SceneView &s, const u
     const float ezB = czB * inv.z + (-pzB * inv.z);
     const float tnB = tB + gmax(gmin(exB, gmin(eyB, ezB)), 0.01f);
     const float tB2 = (idB == 0) ? tnB : tB;
-    const bool hitB = voxB != 0;
-    const bool doneB = hitB || outB || !(tB2 < 128.0f);
-    t = doneA ? tA2 : tB2;
-    t_pre = doneA ? tA : tB;
-    hit = doneA ? hitA : hitB;
-    steps = doneA ? 1 : 2;
-    return doneA || doneB;
-}
-
-// ---- the same pair of steps with the NEXT pair's first block id already requested (opt-in: -DLUMCU_ROLL) ------
-// Roll carries the front half of the step that follows: the sample position at t + 0.5 and its block id (0 when the
-// position is outside the world).  In steady state a pair of steps then waits for two fetch latencies
-// (voxel_A | id_B, voxel_B | id_C) instead of three.  roll_prime() fills it for a ray that was just (re)loaded.
-struct Roll { float px, py, pz; int id; };
-
-__device__ __forceinline__ void roll_prime(const SceneView &s, const uint3 &wsbits, const f3 &o, const f3 &d, float t, Roll &r) {
-    const float tA = t + 0.5f;
-    r.px = o.x + d.x * tA; r.py = o.y + d.y * tA; r.pz = o.z + d.z * tA;
-    const bool out = __float_as_uint(r.px) >= wsbits.x || __float_as_uint(r.py) >= wsbits.y || __float_as_uint(r.pz) >= wsbits.z;
-    r.id = 0;
-    if (!out) r.id = __ldg(s.world + ((f2i(r.px) >> 4) + s.wx * ((f2i(r.py) >> 4) + s.wy * (f2i(r.pz) >> 4))));
-}
-
-__device__ __forceinline__ bool march_two_steps_rolling(const SceneView &s, const uint3 &wsbits, const f3 &o, const f3 &d,
-                                                        const f3 &inv, const i3 &cm, float &t, float &t_pre, bool &hit,
-                                                        int &steps, Roll &r) {
-    // step A: position and block id were produced by the previous pair (or by roll_prime)
-    const float tA = t + 0.5f;
-    const float pxA = r.px, pyA = r.py, pzA = r.pz;
-    const bool outA = __float_as_uint(pxA) >= wsbits.x || __float_as_uint(pyA) >= wsbits.y || __float_as_uint(pzA) >= wsbits.z;
-    const int ixA = f2i(pxA), iyA = f2i(pyA), izA = f2i(pzA);
-    const int bxA = ixA >> 4, byA = iyA >> 4, bzA = izA >> 4;
-    const int idA = r.id;
-    const int VA = mad16(mad16(ixA, iyA), izA), BA = mad16(mad16(bxA, byA), bzA);
-    int voxA = 0;
-    if (idA != 0) voxA = __ldg(s.bricks + (uint32_t)(idA * 4096 + msub16(BA, VA)));
-    const float cxA = __int_as_float(mad16(bxA, cm.x)) - 8388608.0f;
-    const float cyA = __int_as_float(mad16(byA, cm.y)) - 8388608.0f;
-    const float czA = __int_as_float(mad16(bzA, cm.z)) - 8388608.0f;
-    const float exA = cxA * inv.x + (-pxA * inv.x);
-    const float eyA = cyA * inv.y + (-pyA * inv.y);
-    const float ezA = czA * inv.z + (-pzA * inv.z);
-    const float tnA = tA + gmax(gmin(exA, gmin(eyA, ezA)), 0.01f);
-    const float tA2 = (idA == 0) ? tnA : tA;
-    // step B up to its block id
-    const float tB = tA2 + 0.5f;
-    const float pxB = o.x + d.x * tB, pyB = o.y + d.y * tB, pzB = o.z + d.z * tB;
-    const bool outB = __float_as_uint(pxB) >= wsbits.x || __float_as_uint(pyB) >= wsbits.y || __float_as_uint(pzB) >= wsbits.z;
-    const int ixB = f2i(pxB), iyB = f2i(pyB), izB = f2i(pzB);
-    const int bxB = ixB >> 4, byB = iyB >> 4, bzB = izB >> 4;
-    int idB = 0;
-    if (!outB) idB = __ldg(s.world + (bxB + s.wx * (byB + s.wy * bzB)));
-    const bool hitA = voxA != 0;
-    const bool doneA = hitA || outA || !(tA2 < 128.0f);
-    const int VB = mad16(mad16(ixB, iyB), izB), BB = mad16(mad16(bxB, byB), bzB);
-    int voxB = 0;
-    if (idB != 0 && !doneA) voxB = __ldg(s.bricks + (uint32_t)(idB * 4096 + msub16(BB, VB)));
-    const float cxB = __int_as_float(mad16(bxB, cm.x)) - 8388608.0f;
-    const float cyB = __int_as_float(mad16(byB, cm.y)) - 8388608.0f;
-    const float czB = __int_as_float(mad16(bzB, cm.z)) - 8388608.0f;
-    const float exB = cxB * inv.x + (-pxB * inv.x);
-    const float eyB = cyB * inv.y + (-pyB * inv.y);
-    const float ezB = czB * inv.z + (-pzB * inv.z);
-    const float tnB = tB + gmax(gmin(exB, gmin(eyB, ezB)), 0.01f);
-    const float tB2 = (idB == 0) ? tnB : tB;
-    // front half of the step after B (needs B's block id, not B's voxel): what the next call starts from
-    const float tC = tB2 + 0.5f;
-    const float pxC = o.x + d.x * tC, pyC = o.y + d.y * tC, pzC = o.z + d.z * tC;
-    const bool outC = __float_as_uint(pxC) >= wsbits.x || __float_as_uint(pyC) >= wsbits.y || __float_as_uint(pzC) >= wsbits.z;
-    int idC = 0;
-    if (!outC && !doneA) idC = __ldg(s.world + ((f2i(pxC) >> 4) + s.wx * ((f2i(pyC) >> 4) + s.wy * (f2i(pzC) >> 4))));
-    r.px = pxC; r.py = pyC; r.pz = pzC; r.id = idC;
     const bool hitB = voxB != 0;
     const bool doneB = hitB || outB || !(tB2 < 128.0f);
     t = doneA ? tA2 : tB2;
@@ -443,47 +370,6 @@ __device__ __forceinline__ void refine_hit(const SceneView &s, const f3 &o, cons
     f3 tDelta = {fabsf(inv.x), fabsf(inv.y), fabsf(inv.z)};   // 1/|d| == |1/d| exactly
     int vx = f2i(h.x), vy = f2i(h.y), vz = f2i(h.z);
     float ax = 0.0f, ay = 0.0f, az = 0.0f;
-#ifdef LUMCU_REFINE_AHEAD     // opt-in until measured
-    if constexpr (VALID) {
-        // The voxels the DDA visits do not depend on the fetched data, so the block id of voxel k+1 is requested
-        // while voxel k is still in flight: one fetch latency per step instead of two.  id < 0 marks a voxel outside
-        // the world, which takes the general get_voxel.  Same fetch results, same step order as the loop below.
-        const unsigned ex = (unsigned)(s.wx << 4), ey = (unsigned)(s.wy << 4), ez = (unsigned)(s.wz << 4);
-        auto block_id = [&](int x, int y, int z) -> int {
-            int id = -1;
-            if ((unsigned)x < ex && (unsigned)y < ey && (unsigned)z < ez)
-                id = __ldg(s.world + ((x >> 4) + s.wx * ((y >> 4) + s.wy * (z >> 4))));
-            return id;
-        };
-        auto voxel_of = [&](int id, int x, int y, int z) -> int {
-            if (id < 0) { int b; return get_voxel(s, x, y, z, b); }
-            int v = 0;
-            if (id != 0) v = __ldg(s.bricks + (uint32_t)(id * 4096 + (((x & 15) << 8) | ((y & 15) << 4) | (z & 15))));
-            return v;
-        };
-        int id = block_id(vx, vy, vz);
-        int ns = 0, it = 0;
-        for (;;) {
-            const int pending = voxel_of(id, vx, vy, vz);         // voxel k: in flight
-            const float nax = ((tMax.x <= tMax.y) && (tMax.x <= tMax.z)) ? 1.0f : 0.0f;
-            const float nay = ((tMax.x >= tMax.y) && (tMax.y <= tMax.z)) ? 1.0f : 0.0f;
-            const float naz = ((tMax.z <= tMax.x) && (tMax.z <= tMax.y)) ? 1.0f : 0.0f;
-            const int nx = vx + stx * (int)nax, ny = vy + sty * (int)nay, nz = vz + stz * (int)naz;
-            const int nid = block_id(nx, ny, nz);                 // block id of voxel k+1: in flight with it
-            vid = pending;
-            ns++;
-            if (!((it++ <= 4) && (vid == 0))) break;
-            ax = nax; ay = nay; az = naz;
-            vx = nx; vy = ny; vz = nz;
-            tMax.x += tDelta.x * ax; tMax.y += tDelta.y * ay; tMax.z += tDelta.z * az;
-            id = nid;
-        }
-        refine_samples = ns;
-        n = {-((float)stx * ax), -((float)sty * ay), -((float)stz * az)};
-        tf = (tMax.x - tDelta.x) * ax + (tMax.y - tDelta.y) * ay + (tMax.z - tDelta.z) * az;
-        return;
-    }
-#endif
     vid = get_voxel_v<VALID>(s, vx, vy, vz);
     int ns = 1;
     int it = 0;
@@ -543,12 +429,8 @@ __device__ __forceinline__ bool march_ray(const SceneView &s, const MarchConsts 
         const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
         float t_pre;
         bool hit;
-#ifdef LUMCU_SPEC2_WG     // opt-in until measured: the fused two-step march for the one-thread-per-ray kernels too
-        int steps;
+        int steps;     // the fused pair of steps here too (demo world: 34 -> 32 us per update, r02 sweep)
         while (!march_two_steps_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit, steps)) {}
-#else
-        while (!march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit)) {}
-#endif
         if (hit) return true;
         // Ended without an in-world hit.  Unlike the probe rays, whose origins are built by setup_ray, these
         // origins come from the caller: a position of -0.0 or NaN is "out" for the bit test but not for
@@ -587,12 +469,8 @@ __device__ __forceinline__ RayResult trace_probe_ray(const SceneView &s, int px,
         const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
         float t_pre;
         bool done;
-#ifdef LUMCU_SPEC2_WG
         int steps;
         do { done = march_two_steps_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit, steps); samples += steps; } while (!done);
-#else
-        do { done = march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit); samples++; } while (!done);
-#endif
         if (!hit && resolve_pending(s, mc, o, d, t_pre)) { hit = true; t = t_pre; }
     } else {
         int st;

@@ -117,9 +117,6 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
 // own (o, d, t) only, and the reduction tree is fixed.
 struct PoolRay {
     f3 o, d, inv; float t; int ns; i3 cm;
-#ifdef LUMCU_ROLL
-    Roll roll;      // front half of the ray's next step (march_two_steps_rolling)
-#endif
 };
 
 // Ray slots, packed for 16-byte shared-memory accesses: a = (o.xyz, t), b = (d.xyz, inv.x),
@@ -181,9 +178,6 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                     if (pos < limit) {
                         cur = src ? (int)src[pos] : pos;
                         sm.load(cur, q);
-#ifdef LUMCU_ROLL
-                        if constexpr (FAST) roll_prime(s, wsbits, q.o, q.d, q.t, q.roll);
-#endif
                     }
                 }
                 exhausted = base + cnt >= limit;
@@ -209,45 +203,28 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
         }
         // Two march steps per refill check: with the 62-instruction step the ballot / refill / exit logic above is a
         // quarter of an iteration, and a lane that ends in the first step idles for one step only (B200, C4 world:
-        // 1 step 20.55 ms, 2 steps 19.84, 3 steps 20.34, 4 steps 21.60).
-#ifndef LUMCU_STEPS
-#define LUMCU_STEPS 2
-#endif
-#if !defined(LUMCU_NO_SPEC2) && LUMCU_STEPS == 2
+        // 1 step 20.55 ms, 2 steps 19.84, 3 steps 20.34, 4 steps 21.60; the pair fused, march_two_steps_fast: 18.96).
         if constexpr (FAST) {
             if (cur >= 0) {
                 bool hit;
                 float t_end;
                 int steps;
-#ifdef LUMCU_ROLL
-                const bool done = march_two_steps_rolling(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit, steps, q.roll);
-#else
                 const bool done = march_two_steps_fast(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit, steps);
-#endif
                 q.ns += steps;
                 if (done) {
-                    sm.a[cur].w = hit ? q.t : -t_end;
+                    sm.a[cur].w = hit ? q.t : -t_end;              // what a ray that ends without a hit stores: -t_pre
                     if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                     cur = -1;
                 }
             }
         } else
-#endif
 #pragma unroll
-        for (int rep = 0; rep < LUMCU_STEPS; rep++)
+        for (int rep = 0; rep < 2; rep++)
         if (cur >= 0) {
-            bool done, hit;
-            float t_end;                                            // what a ray that ends without a hit stores
-            if constexpr (FAST) {
-                done = march_step_fast(s, wsbits, q.o, q.d, q.inv, q.cm, q.t, t_end, hit);
-            } else {
-                const int st = march_step(s, mc, q.o, q.d, q.inv, q.t);
-                done = st != 0; hit = st == 1;
-                t_end = q.t;
-            }
+            const int st = march_step(s, mc, q.o, q.d, q.inv, q.t);
             q.ns++;
-            if (done) {
-                sm.a[cur].w = hit ? q.t : -t_end;                  // sign = no hit (t >= 0.5 always)
+            if (st != 0) {
+                sm.a[cur].w = st == 1 ? q.t : -q.t;                // sign = no hit (t >= 0.5 always)
                 if constexpr (DEBUG) sm.ns[cur] = (unsigned short)q.ns;
                 cur = -1;
             }
@@ -328,40 +305,6 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     __syncthreads();
 
     // ---- phase A: setup ----
-#ifdef LUMCU_HASH_SHARE   // opt-in until measured
-    // The second draw of ray g is the first draw of ray g + 1 (the RNG state only differs in x = gid + seed, and the
-    // second draw increments x): a warp that sets up the 32*RPT contiguous rays of its own pass-0 slice needs RPT + 1
-    // hash evaluations per lane instead of 2*RPT, and takes each ray's second draw from its neighbour lane (lane 31:
-    // from lane 0's next round).  The slice is then written and read by this warp only: __syncwarp, not __syncthreads.
-    {
-        constexpr int ROUNDS = NR / NW / 32;
-        const int first = warp * (NR / NW);
-        const uint32_t useed = (uint32_t)a.time_seed;
-        f3 hk = hash33((uint32_t)(wg0 * R + first + lane) + useed, useed, useed);
-#pragma unroll 1
-        for (int k = 0; k < ROUNDS; k++) {
-            const int r = first + 32 * k + lane;
-            const f3 hn = hash33((uint32_t)(wg0 * R + r + 32) + useed, useed, useed);      // this lane's draw of the next round
-            const f3 give = lane == 0 ? hn : hk;
-            const f3 r2 = {__shfl_sync(FULL, give.x, (lane + 1) & 31), __shfl_sync(FULL, give.y, (lane + 1) & 31),
-                           __shfl_sync(FULL, give.z, (lane + 1) & 31)};
-            if (r < nrays) {
-                const int pr = r / R, ray = r % R;
-                const short4 rq = sm_req[pr];
-                const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
-                f3 o, d, inv;
-                setup_ray_from_draws(rq.x, rq.y, rq.z, ray, fib, hk, r2, o, d, inv);
-                sm.a[r] = make_float4(o.x, o.y, o.z, 0.0f);
-                sm.b[r] = make_float4(d.x, d.y, d.z, inv.x);
-                sm.c[r] = make_float2(inv.y, inv.z);
-                sm.done[r] = 1;
-                if constexpr (DEBUG) sm.ns[r] = 0;
-            }
-            hk = hn;
-        }
-    }
-    __syncwarp();
-#else
     for (int r = tid; r < nrays; r += THREADS) {
         const int pr = r / R, ray = r % R;
         const short4 rq = sm_req[pr];
@@ -376,7 +319,6 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
         if constexpr (DEBUG) sm.ns[r] = 0;
     }
     __syncthreads();
-#endif
 
     // ---- phase B, pass 0: every warp marches ----
     const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
@@ -471,13 +413,8 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     }
 }
 
-#ifdef LUMCU_MINB             // tuning knob: min resident CTAs per SM asked of ptxas (a register cap)
-#define LUMCU_POOL_BOUNDS __launch_bounds__(THREADS, LUMCU_MINB)
-#else
-#define LUMCU_POOL_BOUNDS __launch_bounds__(THREADS)
-#endif
 template <int R, int THREADS, int RPT, bool DEBUG>
-__global__ void LUMCU_POOL_BOUNDS radiance_update_pool_kernel(SceneView s, UpdateArgs a) {
+__global__ void __launch_bounds__(THREADS) radiance_update_pool_kernel(SceneView s, UpdateArgs a) {
     __shared__ PoolCta<R, THREADS, RPT, DEBUG> cta;
     // The fast march needs brick 0 empty and every world id inside the palette; the second is a property of
     // the uploaded data, checked on the device (validate_world_kernel) so that no host sync is needed.

@@ -1,7 +1,7 @@
 """Workload definitions (inputs only, no arithmetic of the path).
 
 demo_scene()       BASELINE.json configs 1-3: Lum's demo world, from the committed fixture
-                   tests/golden/demo_scene.npz (generated from the reference's assets by
+                   lum_b200/data/demo_scene.npz (generated from the reference's assets by
                    tests/golden/make_demo_fixture.py).
 synthetic_scene()  BASELINE.json configs 4-5 (SURVEY.md section 8d "C4 inputs"): dense random
                    world, counter-based splitmix64 so any size is reproducible everywhere.
@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEMO_FIXTURE = os.path.join(ROOT, "tests", "golden", "demo_scene.npz")
+DEMO_FIXTURE = os.path.join(ROOT, "lum_b200", "data", "demo_scene.npz")
 SYNTH_SEED = 0x4C554D31
 
 _M64 = (1 << 64) - 1

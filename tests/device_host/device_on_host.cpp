@@ -3,9 +3,9 @@
 // the host, one "thread" after another, and the workgroup reduction / blend of the kernels restated around them
 // (radiance_kernels.cuh phase D: xor butterfly per <=32-ray subgroup, /SUB, mean of subgroups, mix, pack).
 //   mode 0: general march (march_step)            -- what the kernels run for an unvalidated scene
-//   mode 1: fast march, one step per iteration    -- trace_probe_ray<true>, the one-workgroup-per-CTA kernel
+//   mode 1: trace_probe_ray<true>                 -- the one-workgroup-per-CTA kernel (fused pair of fast steps)
 //   mode 2: fast march, fused two steps           -- march_two_steps_fast, the pooled kernel's loop body
-//   mode 3: the same with a rolling block-id fetch -- march_two_steps_rolling (opt-in, not the default yet)
+//   mode 3: fast march, one step per iteration    -- march_step_fast, what the fused pair is defined against
 // Compiled with g++ -ffp-contract=off (the kernels: nvcc -fmad=false), so one rounding per written operation.
 #include "cuda_host_shim.hpp"
 #include "../../lum_b200/csrc/radiance_device.cuh"
@@ -34,24 +34,17 @@ static RayResult trace_fused(const SceneView &s, int px, int py, int pz, uint32_
     return res;
 }
 
-// mode 3: march_two_steps_rolling (opt-in -DLUMCU_ROLL in the pooled kernel): the next pair's first block id carried along
-static RayResult trace_rolling(const SceneView &s, int px, int py, int pz, uint32_t gid_x, int ray, f3 fib, int time_seed, f3 sun) {
+// mode 3: the fast march one step at a time (march_step_fast, what the fused pair is defined against)
+static RayResult trace_single(const SceneView &s, int px, int py, int pz, uint32_t gid_x, int ray, f3 fib, int time_seed, f3 sun) {
     f3 o, d, inv;
     setup_ray(px, py, pz, gid_x, ray, fib, time_seed, o, d, inv);
     const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
     const uint3 wsbits = {__float_as_uint(mc.wsx), __float_as_uint(mc.wsy), __float_as_uint(mc.wsz)};
     const i3 cm = {0x4B000000 + (d.x > 0.0f ? 16 : 0), 0x4B000000 + (d.y > 0.0f ? 16 : 0), 0x4B000000 + (d.z > 0.0f ? 16 : 0)};
     float t = 0.0f, t_pre = 0.0f;
-    int samples = 0, steps = 0, calls = 0;
+    int samples = 0;
     bool hit = false, done;
-    Roll roll;
-    roll_prime(s, wsbits, o, d, t, roll);
-    do {
-        done = march_two_steps_rolling(s, wsbits, o, d, inv, cm, t, t_pre, hit, steps, roll);
-        samples += steps;
-        // a parked ray goes back to its slot with t only and is primed again when a tail warp picks it up
-        if (!done && (++calls % 3) == 0) roll_prime(s, wsbits, o, d, t, roll);
-    } while (!done);
+    do { done = march_step_fast(s, wsbits, o, d, inv, cm, t, t_pre, hit); samples++; } while (!done);
     if (!hit && resolve_pending(s, mc, o, d, t_pre)) { hit = true; t = t_pre; }
     RayResult res;
     int nr;
@@ -89,7 +82,7 @@ extern "C" int device_on_host_update(int wx, int wy, int wz, int capacity, int b
             if (mode == 0) r = trace_probe_ray<false>(s, rq[0], rq[1], rq[2], gid_x, ray, fib, time_seed, sun);
             else if (mode == 1) r = trace_probe_ray<true>(s, rq[0], rq[1], rq[2], gid_x, ray, fib, time_seed, sun);
             else if (mode == 2) r = trace_fused(s, rq[0], rq[1], rq[2], gid_x, ray, fib, time_seed, sun);
-            else r = trace_rolling(s, rq[0], rq[1], rq[2], gid_x, ray, fib, time_seed, sun);
+            else r = trace_single(s, rq[0], rq[1], rq[2], gid_x, ray, fib, time_seed, sun);
             light[ray] = r.light;
             if (ray_samples) ray_samples[w * R + ray] = (uint32_t)r.samples;
             if (ray_hits) ray_hits[w * R + ray] = r.hit ? 1 : 0;

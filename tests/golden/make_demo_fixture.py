@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/demo_scene.npz from the reference's demo assets.
+"""Generate lum_b200/data/demo_scene.npz (workload data of the package: bench.py and the demos load it) from the reference's demo assets.
 
 Runs ONLY in the build container (needs /root/reference and oracle/_ref/ref_vox_dump, the
 reference's own ogt_vox decoder compiled in place by oracle/Makefile).  The output is the
@@ -61,7 +61,7 @@ def main():
         out[f"model_{name}"] = v
         if name == "tank_body":
             out["materials"] = m
-    path = os.path.join(HERE, "demo_scene.npz")
+    path = os.path.join(HERE, "..", "..", "lum_b200", "data", "demo_scene.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
     ids, cnt = np.unique(world, return_counts=True)

@@ -1,6 +1,6 @@
 """The CUDA kernels' per-thread arithmetic, compiled for the host, against the oracle -- no GPU needed.
 
-lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the march variants -- general, fast, fused, rolling --, pending-sample resolution,
+lum_b200/csrc/radiance_device.cuh (ray setup, RNG, the march variants -- general, fast, fused, single-step --, pending-sample resolution,
 refinement, material fetch, field gather, shading, unorm10 pack/unpack, glossy_fragment and map_model_invocation,
 the bodies of the glossy and map kernels) is compiled with g++ through
 tests/device_host/cuda_host_shim.hpp and run one "thread" after another by tests/device_host/device_on_host.cpp,
@@ -22,7 +22,7 @@ DEPS = [SRC, os.path.join(HERE, "device_host", "cuda_host_shim.hpp"),
 OUT = os.path.join(HERE, "_build", "libdevice_on_host.so")
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
-MODES = {"general": 0, "fast": 1, "fused": 2, "rolling": 3}
+MODES = {"general": 0, "fast": 1, "fused": 2, "single": 3}
 
 
 def build_host_lib(out, defines=()):
@@ -43,14 +43,6 @@ def build_host_lib(out, defines=()):
 @pytest.fixture(scope="module")
 def host_lib():
     return build_host_lib(OUT)
-
-
-@pytest.fixture(scope="module")
-def host_lib_optin():
-    """The compile-time variants that are built but not yet the default: the fused two-step
-    march in the one-thread-per-ray kernels and the one-ahead refinement.  Kept bit-exact here until a GPU round
-    measures them."""
-    return build_host_lib(OUT.replace(".so", "_optin.so"), ("LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD"))
 
 
 def run(lib, O, scn, f0, req, seed, mode, rays=64, size=1, shift=0, reactiveness=0.01):
@@ -116,12 +108,12 @@ def test_synthetic_all_ray_counts(host_lib, oracle_mod, small_synth, rays):
     req = O.build_requests(small_synth["world"])[::7]
     f0 = np.random.default_rng(rays).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
     ref = O.update(sc, f0, req, 11, want_rays=True)
-    for mode in ("fast", "fused", "rolling"):
+    for mode in ("fast", "fused", "single"):
         assert_same(run(host_lib, O, small_synth, f0, req, 11, MODES[mode], rays=rays), ref)
 
 
 def test_synthetic_64x64x16_full_update(host_lib, oracle_mod):
-    """BASELINE configs[4]'s smallest world, whole (65,456 probes, 4.2 M rays), fused and rolling march."""
+    """BASELINE configs[4]'s smallest world, whole (65,456 probes, 4.2 M rays), fused and single-step march."""
     from lum_b200 import scenes
     O = oracle_mod
     syn = scenes.synthetic_scene(64, 64, 16)
@@ -129,7 +121,7 @@ def test_synthetic_64x64x16_full_update(host_lib, oracle_mod):
     req = O.build_requests(syn["world"])
     f0 = np.random.default_rng(0).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
     ref = O.update(sc, f0, req, 7, want_rays=True)
-    for mode in ("fused", "rolling"):
+    for mode in ("fused", "single"):
         assert_same(run(host_lib, O, syn, f0, req, 7, MODES[mode]), ref)
 
 
@@ -160,21 +152,9 @@ def test_random_small_worlds(host_lib, oracle_mod, case):
     shift = int(rng.integers(0, size))
     seed = int(rng.integers(-2 ** 31, 2 ** 31))
     ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=True)
-    modes = ("general", "fast", "fused", "rolling") if not bricks[0].any() else ("general",)
+    modes = ("general", "fast", "fused", "single") if not bricks[0].any() else ("general",)
     for mode in modes:
         assert_same(run(host_lib, O, scn, f0, req, seed, MODES[mode], size=size, shift=shift), ref)
-
-
-@pytest.mark.parametrize("mode", ["fast", "fused"])
-def test_optin_variants_stay_bit_exact(host_lib_optin, oracle_mod, demo, small_synth, mode):
-    """-DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD (off by default): demo world and the dense synthetic world."""
-    O = oracle_mod
-    for scn, stride, rays in ((demo, 1, 64), (small_synth, 5, 64), (small_synth, 11, 16)):
-        sc = scene_of(O, scn, rays=rays)
-        req = O.build_requests(scn["world"])[::stride]
-        f0 = np.random.default_rng(rays + stride).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
-        ref = O.update(sc, f0, req, 9, want_rays=True)
-        assert_same(run(host_lib_optin, O, scn, f0, req, 9, MODES[mode], rays=rays), ref)
 
 
 # ---- the glossy pass: glossy_fragment() is the body of glossy_kernel ------------------------------------------
@@ -208,21 +188,20 @@ def assert_frames_equal(got, ref):
     assert np.array_equal(bits(got)[nz], bits(ref)[nz])
 
 
-@pytest.mark.parametrize("optin", [False, True])
 @pytest.mark.parametrize("tag", ["demo", "demo_all", "synth"])
-def test_glossy_fragment_matches_oracle(host_lib, host_lib_optin, oracle_mod, tag, optin):
+def test_glossy_fragment_matches_oracle(host_lib, oracle_mod, tag):
     """The cases of tests/test_glossy_gpu.py on the host build (default and opt-in march)."""
     from glossy_cases import make_case
     O = oracle_mod
     c = make_case(O, tag)
     ref = O.glossy(c["scene"], c["field"], c["view"], c["mat_norm"], c["depth"])
-    got, cov = run_glossy(host_lib_optin if optin else host_lib, c["scn"], c["field"], c["view"], c["mat_norm"], c["depth"])
+    got, cov = run_glossy(host_lib, c["scn"], c["field"], c["view"], c["mat_norm"], c["depth"])
     assert np.array_equal(cov, ref["covered"]) and cov.any()
     assert_frames_equal(got, ref["frame"])
 
 
 @pytest.mark.parametrize("seed", range(4))
-def test_glossy_fragment_random_gbuffers(host_lib, host_lib_optin, oracle_mod, seed):
+def test_glossy_fragment_random_gbuffers(host_lib, oracle_mod, seed):
     """Arbitrary G-buffers (origins inside solids and outside the world, unnormalised normals); seed 3 loads a
     brick 0 (general march)."""
     from glossy_cases import make_case
@@ -238,7 +217,7 @@ def test_glossy_fragment_random_gbuffers(host_lib, host_lib_optin, oracle_mod, s
     dp = rng.random((h, w), dtype=np.float32) * np.float32(0.6)
     view = O.camera_view((rng.random(3) * 300 - 50), (0.3 + seed, 0.9 - seed, -0.6), w, h, pixels_in_voxel=0.2)
     ref = O.glossy(sc, c["field"], view, mn, dp)
-    for lib in (host_lib, host_lib_optin):
+    for lib in (host_lib,):
         got, cov = run_glossy(lib, scn, c["field"], view, mn, dp)
         assert np.array_equal(cov, ref["covered"]) and cov.any()
         assert_frames_equal(got, ref["frame"])

@@ -47,13 +47,6 @@ def emu():
     return build(OUT)
 
 
-@pytest.fixture(scope="module")
-def emu_optin():
-    """The compile-time variants that are not the default yet, all at once: here their kernel
-    integration runs -- e.g. the rolling block-id fetch being primed at every refill and again for a parked ray."""
-    return build(OUT.replace(".so", "_optin.so"), ("LUMCU_ROLL", "LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD", "LUMCU_HASH_SHARE"))
-
-
 def run(lib, O, scn, f0, req, seed, variant, rays=64, size=1, shift=0, reactiveness=0.01):
     world = np.ascontiguousarray(scn["world"], np.int16)
     bricks = np.ascontiguousarray(scn["bricks"], np.uint8)
@@ -139,18 +132,6 @@ def test_fuzz_worlds_kernels(emu, oracle_mod, case):
         check(emu, O, scn, req, seed, variant, size=size, shift=shift, field_seed=case)
 
 
-@pytest.mark.parametrize("variant", [POOL, WG], ids=["pooled", "workgroup"])
-def test_optin_variants_kernel_integration(emu_optin, oracle_mod, demo, small_synth, variant):
-    """-DLUMCU_ROLL -DLUMCU_SPEC2_WG -DLUMCU_REFINE_AHEAD -DLUMCU_HASH_SHARE (off by default) through the real
-    kernels; 43 and 20 probes leave a ragged last batch, rays = 16 and 256 change the probes per batch."""
-    O = oracle_mod
-    check(emu_optin, O, demo, O.build_requests(demo["world"])[1000:1043], 5, variant)
-    check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:20], 11, variant)
-    if variant == POOL:
-        check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:29], -3, variant, rays=16)
-        check(emu_optin, O, small_synth, O.build_requests(small_synth["world"])[::97][:5], 77, variant, rays=256)
-
-
 def test_request_builder_kernels(emu, oracle_mod, demo):
     """SURVEY a13 on the emulator: build_count / build_scan / build_scatter / build_specials against the oracle's list
     (demo world: 2,689 requests in z,y,x order; specials appended in submission order unless already selected)."""
@@ -185,9 +166,7 @@ def test_shift_kernel(emu, oracle_mod, d):
     assert np.array_equal(got, np.asarray(ref).reshape(-1))
 
 
-@pytest.mark.parametrize("defines", [(), ("LUMCU_ROLL", "LUMCU_SPEC2_WG", "LUMCU_REFINE_AHEAD", "LUMCU_HASH_SHARE")],
-                         ids=["default", "optin"])
-def test_emulated_kernels_are_race_free_under_tsan(defines):
+def test_emulated_kernels_are_race_free_under_tsan(defines=()):
     """Host-side racecheck: tests/device_host/tsan_main.cpp runs the emulated pooled and per-workgroup kernels (dense
     random world: refill, parking, tail passes) under ThreadSanitizer.  Every CUDA thread is an OS thread and every
     barrier / warp collective a real synchronisation, so a missing __syncthreads / __syncwarp in the kernels is a

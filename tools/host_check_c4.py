@@ -2,7 +2,7 @@
 """The whole C4 update (4,191,908 probes x 64 rays of the synthetic 256x256x64 world, random field, seed 7) with the
 kernels' per-thread source compiled for the host (tests/device_host) against the oracle, bit for bit -- every march
 variant.  No GPU needed; about a minute per variant on 8 cores.  Test infrastructure, not a product path.
-usage: host_check_c4.py [fast fused rolling general]"""
+usage: host_check_c4.py [fast fused single general]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -11,7 +11,7 @@ import oracle as O
 import test_device_source_on_host as T
 from lum_b200 import scenes
 
-modes = sys.argv[1:] or ["fast", "fused", "rolling"]
+modes = sys.argv[1:] or ["fast", "fused", "single"]
 lib = T.build_host_lib(T.OUT)
 syn = scenes.synthetic_scene(256, 256, 64)
 sc = T.scene_of(O, syn)
