@@ -53,18 +53,19 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic(workload, n_gpus):
-    """DRAM bytes per launch of the trace kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
-    `ncu --set full` capture, profiles/roofline_traffic.json, written by tools/ncu_traffic.py).
-    Only the single-GPU launch was captured; None otherwise."""
-    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+def load_profile_evidence(workload, n_gpus, rays):
+    """What one `ncu --set full` capture of the trace kernel on this workload says (profiles/roofline_evidence.json,
+    written by tools/ncu_evidence.py from the .ncu-rep; the file names the capture it came from): DRAM bytes per
+    launch (roofline.traffic), issue-slot and lane utilisation, achieved L1 / L2 sector rates -- next to the
+    ceilings of this access pattern measured by tools/gather_ceiling.cu (profiles/r02_gather_ceiling.json).
+    Only single-GPU launches at 64 rays per probe were captured; {} otherwise."""
+    if n_gpus != 1 or rays != 64:
+        return {}
     try:
-        t = json.load(open(p))
-        if n_gpus == 1 and workload in t:
-            return float(t[workload]["dram_bytes_per_launch"])
+        ev = json.load(open(os.path.join(ROOT, "profiles", "roofline_evidence.json"))).get(workload)
+        return ev or {}
     except Exception:
-        pass
-    return None
+        return {}
 
 
 def make_scene(workload):
@@ -135,7 +136,7 @@ class ClockSampler:
 class Runner:
     """One rank's stage + the per-step sequences (value region and e2e region)."""
 
-    def __init__(self, scene, device, rank, world_size, torch, dist, exchange="fused"):
+    def __init__(self, scene, device, rank, world_size, torch, dist, exchange="fused", rays=RAYS):
         import lum_b200
         from lum_b200 import distributed as D
         self.D = D
@@ -146,7 +147,9 @@ class Runner:
         if wz % world_size:
             raise SystemExit(f"world z={wz} not divisible by {world_size} ranks")
         self.z0, self.z1 = D.slab_bounds(wz, rank, world_size)
-        self.st = lum_b200.RadianceStage((wx, wy, wz), scene["bricks"].shape[0], rays_per_probe=RAYS, device=device)
+        self.rays = rays
+        self.device = device
+        self.st = lum_b200.RadianceStage((wx, wy, wz), scene["bricks"].shape[0], rays_per_probe=rays, device=device)
         self.st.upload_world(scene["world"])
         self.st.upload_bricks(0, scene["bricks"])
         self.st.upload_materials(scene["materials"])
@@ -159,10 +162,11 @@ class Runner:
         # e2e host buffers live in pinned memory (the contract's "from pinned host memory"): the world
         # goes up without a staging copy and the field comes down at full PCIe rate
         self._pin_w = torch.empty(self.cells, dtype=torch.int16, pin_memory=True)
-        self._pin_f = torch.empty(self.cells, dtype=torch.int32, pin_memory=True)
+        self._pin_f = torch.empty(2 * self.cells, dtype=torch.int32, pin_memory=True)     # one result buffer per frame in flight
         self.world_host = self._pin_w.numpy()
         self.world_host[:] = np.ascontiguousarray(scene["world"], np.int16).reshape(-1)
-        self.field_host = self._pin_f.numpy().view(np.uint32)
+        self.field_host = self._pin_f.numpy().view(np.uint32)[:self.cells]
+        self.field_host2 = [self._pin_f.numpy().view(np.uint32)[:self.cells], self._pin_f.numpy().view(np.uint32)[self.cells:]]
         self.zero_field = np.zeros(self.cells, np.uint32)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{device}")   # > 126 MB L2
         self.fused = False
@@ -178,7 +182,7 @@ class Runner:
         if self.fused:
             self.st.peers_close()
             self.fused = False
-        self.world_host = self.field_host = None
+        self.world_host = self.field_host = self.field_host2 = None
         self._pin_w = self._pin_f = None
         self.field_t = self.flush = None
         self.torch.cuda.synchronize()
@@ -212,42 +216,91 @@ class Runner:
             self.st.update(seed, 1, 0)
 
     def step_e2e(self, seed):
-        self.st.upload_world(self.world_host)                 # H2D: world (end_blockify/exec_copies)
-        self.st.build_requests()                              # device builder (+8 B count readback)
+        """One frame through the C-ABI with HOST buffers, queued without waiting for the GPU: world H2D from pinned
+        memory (end_blockify/exec_copies), device-side request build (the count stays on the device), update
+        (+ exchange), D2H of the result into pinned memory (each rank reads its slab at N > 1), a fence.  Like the
+        reference (fif = 2, al.cpp:315-317) two frames are in flight: the host waits for the PREVIOUS frame's fence,
+        so the copies of one frame overlap the tracing of its neighbours.  Everything is inside the timed region."""
+        slot = seed & 1
+        self.st.wait_fence(slot)                              # the frame that last used this result buffer is done
+        self.st.upload_world_async(self.world_host)           # H2D
+        self.st.build_requests(sync=False)
         self.step_resident(seed)
-        if self.n > 1:                                        # D2H: each rank reads its slab of the result
-            lo, hi = self.rank * self.slab_cells, (self.rank + 1) * self.slab_cells
-            with self.torch.cuda.stream(self.stream):
-                self._pin_f[lo:hi].copy_(self.field_t[lo:hi], non_blocking=True)
-            self.st.wait_idle()
-            return self.field_host[lo:hi]
-        self.st.download_field(self.field_host)
-        return self.field_host
+        lo, hi = (self.rank * self.slab_cells, (self.rank + 1) * self.slab_cells) if self.n > 1 else (0, self.cells)
+        self.st.download_field_async(self.field_host2[slot][lo:hi], lo, hi - lo)      # D2H
+        self.st.record_fence(slot)
+        return self.field_host2[slot][lo:hi]
 
-    def timed(self, fn, steps, warmup, first_seed=0):
+    def drain(self):
+        self.st.wait_fence(0); self.st.wait_fence(1)
+
+    def parity_check(self, frames=3):
+        """N > 1: `frames` frames from a fixed pseudo-random field, sharded + exchanged the way the timed steps are,
+        against the same frames unsharded on rank 0 (a scratch single-GPU stage): every replica is compared with
+        rank 0's unsharded result word for word."""
+        torch, dist = self.torch, self.dist
+        f0 = (np.random.default_rng(20261018).integers(0, 2 ** 32, self.cells, dtype=np.uint64).astype(np.uint32) | np.uint32(0xC0000000))
+        self.st.wait_idle(); dist.barrier()
+        self.st.upload_field(f0); self.st.wait_idle(); dist.barrier()
+        for f in range(frames):
+            self.step_resident(1000 + f)
+        self.st.wait_idle(); dist.barrier()
+        mine = torch.from_numpy(self.st.download_field().view(np.int32)).to(self.field_t.device)
+        ref = torch.empty_like(mine)
+        if self.rank == 0:
+            import lum_b200
+            wx, wy, wz = self.dims
+            st1 = lum_b200.RadianceStage((wx, wy, wz), self.scene["bricks"].shape[0], rays_per_probe=self.rays, device=self.device)
+            st1.upload_world(self.scene["world"]); st1.upload_bricks(0, self.scene["bricks"]); st1.upload_materials(self.scene["materials"])
+            st1.build_requests(); st1.upload_field(f0)
+            for f in range(frames):
+                st1.update(1000 + f)
+            ref = torch.from_numpy(st1.download_field().view(np.int32)).to(self.field_t.device)
+            st1.close()
+        dist.broadcast(ref, src=0)
+        equal = torch.tensor([int(torch.equal(mine, ref))], dtype=torch.int32, device=self.field_t.device)
+        differing = torch.tensor([int((mine != ref).sum().item())], dtype=torch.int64, device=self.field_t.device)
+        dist.all_reduce(equal, op=dist.ReduceOp.MIN)
+        dist.all_reduce(differing, op=dist.ReduceOp.MAX)
+        return {"checked": True, "equal": bool(equal.item()), "frames": frames, "replicas_compared": self.n,
+                "words_per_replica": self.cells, "max_differing_words": int(differing.item()),
+                "against": "the same frames unsharded on rank 0 (lumcu_update, scratch stage), random initial field"}
+
+    def timed(self, fn, steps, warmup, first_seed=0, span=False):
         """W untimed + K timed steps; per-step CUDA events on the stage stream, L2 flushed in
-        between (outside the events); returns (total_ms_max_over_ranks, per_step_ms list)."""
+        between (outside the events); returns (total_ms_max_over_ranks, per_step_ms list).
+        span=False: total = sum of the per-step event pairs (each step's work, queued back to back).
+        span=True (the pipelined e2e steps, whose host side waits on fences): total = first step's start to the
+        last step's end minus the L2 flushes (each bracketed by its own event pair), so that any time the GPU sat
+        idle waiting for the host is counted."""
         torch, dist = self.torch, self.dist
         self.reset()
         for i in range(warmup):
             fn(first_seed + i)
+        self.drain()
         with torch.cuda.stream(self.stream):
             ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
             torch.cuda.synchronize()
             if self.n > 1:
                 dist.barrier()
             torch.cuda.synchronize()
+            fl = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
             for k in range(steps):
+                fl[k][0].record(self.stream)
                 self.flush_l2(k)                              # L2 flush on the same stream, outside the events
+                fl[k][1].record(self.stream)
                 ev[k][0].record(self.stream)
                 fn(first_seed + warmup + k)
                 ev[k][1].record(self.stream)
+            self.drain()
             torch.cuda.synchronize()
             if self.n > 1:
                 dist.barrier()
             torch.cuda.synchronize()
         per = [a.elapsed_time(b) for a, b in ev]
         total = float(sum(per))
+        if span:
+            total = float(ev[0][0].elapsed_time(ev[-1][1]) - sum(a.elapsed_time(b) for a, b in fl[1:]))
         if self.n > 1:
             t = torch.tensor([total], dtype=torch.float64, device=self.field_t.device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,7 +335,7 @@ class Runner:
 def measure(runner, steps, warmup, peak):
     """value / e2e / roofline for one workload on this rank set."""
     st = runner.st
-    total_rays = runner.nreq * RAYS
+    total_rays = runner.nreq * runner.rays
     # device-resident
     l0 = st.launch_count()
     total_ms, per = runner.timed(runner.step_resident, steps, warmup)
@@ -306,13 +359,13 @@ def measure(runner, steps, warmup, peak):
     kt = kernel_ms if kernel_ms else ms_per_step
     achieved = alg_bytes / (kt * 1e-3) / 1e9
     # end to end
-    e2e_ms, _ = runner.timed(runner.step_e2e, steps, warmup)
+    e2e_ms, _ = runner.timed(runner.step_e2e, steps, warmup, span=True)
     e2e_value = total_rays / (e2e_ms / steps * 1e-3)
     world_bytes = runner.world_host.nbytes
     return dict(value=value, ms_per_step=ms_per_step, per_step_ms=per, kernel_ms=kernel_ms,
                 alg_bytes=alg_bytes, achieved=achieved, frac=achieved / peak,
-                e2e_value=e2e_value, e2e_ms=e2e_ms / steps, h2d=world_bytes,
-                d2h=runner.cells * 4 // runner.n * runner.n + 8, launches=launches_timed,
+                e2e_value=e2e_value, e2e_ms=e2e_ms / steps, h2d=world_bytes * runner.n,      # every rank uploads the world
+                d2h=runner.cells * 4 // runner.n * runner.n, launches=launches_timed,       # each rank reads its slab back
                 probes=runner.nreq, rays=total_rays)
 
 
@@ -433,11 +486,11 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_baseline(scene, budget_s, threads=0):
+def cpu_baseline(scene, budget_s, threads=0, rays=RAYS):
     """The oracle port on the host cores, on a bounded strided sample of the request list."""
     import oracle as O
     threads = threads or host_threads()
-    sc = O.Scene(scene["world"], scene["bricks"], scene["materials"], rays_per_probe=RAYS)
+    sc = O.Scene(scene["world"], scene["bricks"], scene["materials"], rays_per_probe=rays)
     req = O.build_requests(scene["world"])
     f0 = np.zeros(sc.cells, np.uint32)
     probe = req[:: max(1, len(req) // 2048)][:2048]
@@ -450,7 +503,7 @@ def cpu_baseline(scene, budget_s, threads=0):
     t0 = time.perf_counter()
     r = O.update(sc, f0, sample, 1, nthreads=threads)
     dt = time.perf_counter() - t0
-    return dict(value=len(sample) * RAYS / dt, unit=UNIT, cores=int(r["threads"]), kind="port",
+    return dict(value=len(sample) * rays / dt, unit=UNIT, cores=int(r["threads"]), kind="port",
                 sample=f"{len(sample)} of {len(req)} probes (every {max(1, len(req) // n)}-th request, "
                        f"time_seed 1, zero field), {dt:.2f} s wall, OpenMP over probes"), sample, sc, f0
 
@@ -458,13 +511,15 @@ def cpu_baseline(scene, budget_s, threads=0):
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path = the oracle port
     (the reference's own radiance.comp cannot execute here: no Vulkan)."""
+    global RAYS
     if rank != 0:
         return
     import oracle as O
     scene = make_scene(args.workload)
     nsteps = args.steps + args.warmup
     budget = max(1.0, min(20.0, 150.0 / max(1, nsteps)))
-    base, sample, sc, f0 = cpu_baseline(scene, budget)
+    base, sample, sc, f0 = cpu_baseline(scene, budget, rays=args.rays_per_probe)
+    RAYS = args.rays_per_probe
     for i in range(args.warmup):
         O.update(sc, f0, sample, i, nthreads=host_threads())
     t0 = time.perf_counter()
@@ -485,7 +540,7 @@ def run_reference(args, rank):
     # reference tree exists).  It is NOT the timed arm: the GLSL shim runs every invocation twice (subgroupAdd
     # is resolved in two passes) and its requests are i8vec4, so only probes with coordinates <= 127 qualify.
     try:
-        if O.ref_glsl_available():
+        if O.ref_glsl_available() and RAYS == 64:
             sub = sample[(sample[:, :3].max(axis=1) <= 127)][:256]
             if len(sub):
                 t0 = time.perf_counter()
@@ -498,6 +553,33 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+KERNEL_NAMES = {True: "lumcu::radiance_update_pool_kernel<{r}, {t}, 3, false>", False: "lumcu::radiance_update_wg_kernel<{r}, false>"}
+
+
+def roofline_object(workload, world_size, rays, m, peak, peak_src, scene, runner):
+    """The contract's roofline object for the dominant kernel (the trace kernel), plus what the counters say the
+    kernel is really limited by.  achieved/frac: algorithmic bytes (3*S + 52*H + 12*N, S and H counted by the
+    instrumented kernel in this run) over the kernel time measured in this run (CUDA events on the stage's stream),
+    against the measured HBM peak.  Every other number comes from a file under profiles/ and says which."""
+    pooled = m["rays"] // max(1, world_size) >= (1 << 23)
+    ev = load_profile_evidence(workload, world_size, rays)
+    ro = {"bound": "hbm", "achieved": m["achieved"], "peak": peak, "unit": "GB/s", "frac": m["frac"],
+          "traffic": ev.get("dram_bytes_per_launch"), "peak_source": peak_src,
+          "kernel": KERNEL_NAMES[pooled].format(r=rays, t=256 if rays == 256 else 128), "kernel_ms": m["kernel_ms"],
+          "algorithmic_bytes_per_launch": m["alg_bytes"],
+          # SURVEY 8d's second figure: what one update must touch at least once
+          "compulsory_unique_bytes": int(scene["world"].nbytes + scene["bricks"].nbytes + 6144 + 2 * runner.cells * 4)}
+    if ev:
+        # the formal bound of the contract is HBM, but the working set is L2-resident: the capture shows what limits it
+        ro["limiter"] = ev.get("limiter")
+        ro["issue_active"] = ev.get("issue_active")
+        ro["lanes_active"] = ev.get("lanes_active")
+        ro["l1"] = ev.get("l1")
+        ro["l2"] = ev.get("l2")
+        ro["evidence"] = ev.get("source")
+    return ro
+
+
 def run_ours(args, rank, local_rank, world_size):
     import torch
     import torch.distributed as dist
@@ -508,14 +590,21 @@ def run_ours(args, rank, local_rank, world_size):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     peak, peak_src = load_peaks()
     scene = make_scene(args.workload)
-    runner = Runner(scene, local_rank, rank, world_size, torch, dist, exchange=args.exchange)
+    rays = args.rays_per_probe
+    runner = Runner(scene, local_rank, rank, world_size, torch, dist, exchange=args.exchange, rays=rays)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     m = measure(runner, args.steps, args.warmup, peak)
     clocks = sampler.stop() if rank == 0 else None
     extra = {}
-    if rank == 0 and world_size == 1 and args.workload != "demo" and not args.no_demo:
+    if world_size > 1:
+        # correctness of the sharded + exchanged frames, on the hardware and in the run that is being reported
+        par = runner.parity_check()
+        if rank == 0:
+            par["exchange"] = "fused (NVLink peer stores + flag barrier)" if runner.fused else "nccl all-gather"
+            extra["multi_gpu_parity"] = par
+    if rank == 0 and world_size == 1 and args.workload != "demo" and not args.no_demo and rays == 64:
         dr = Runner(make_scene("demo"), local_rank, 0, 1, torch, dist)
         dm = measure(dr, max(args.steps, 20), max(args.warmup, 5), peak)
         dr.close()
@@ -535,29 +624,24 @@ def run_ours(args, rank, local_rank, world_size):
                          "e2e": {"value": dm["e2e_value"], "unit": UNIT, "ms_per_step": dm["e2e_ms"],
                                  "h2d_bytes_per_step": dm["h2d"], "d2h_bytes_per_step": dm["d2h"]},
                          "roofline": {"bound": "hbm", "achieved": dm["achieved"], "peak": peak, "unit": "GB/s",
-                                      "frac": dm["frac"], "traffic": load_traffic("demo", 1)}}
+                                      "frac": dm["frac"], "traffic": load_profile_evidence("demo", 1, 64).get("dram_bytes_per_launch")}}
     if rank == 0:
         cb = None
         if world_size == 1 and not args.no_cpu:
-            cb = cpu_baseline(scene, 12.0)[0]
+            cb = cpu_baseline(scene, 12.0, rays=rays)[0]
         line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world_size,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": RAYS,
-                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + ("interleaved chunks of 3072, commit fused with the exchange (NVLink peer stores, flag barriers)"
+                "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": rays,
+                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + ("interleaved chunks of 3072; the trace kernel stores each new texel into every rank's inbox over NVLink, one flag barrier, local commit"
                                                                              if runner.fused else "z-slabs + NCCL field all-gather"))
                            if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
                            "time_seed": "step index", "initial_field": "zero"},
                 "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"],
                         "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
                 "gpu_launches": m["launches"],
-                "roofline": {"bound": "hbm", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
-                             "frac": m["frac"], "traffic": load_traffic(args.workload, world_size), "peak_source": peak_src,
-                             "kernel": "radiance_update kernel", "kernel_ms": m["kernel_ms"],
-                             "algorithmic_bytes_per_launch": m["alg_bytes"],
-                             # SURVEY 8d's second figure: what one update must touch at least once
-                             "compulsory_unique_bytes": int(scene["world"].nbytes + scene["bricks"].nbytes + 6144 + 2 * runner.cells * 4)},
+                "roofline": roofline_object(args.workload, world_size, rays, m, peak, peak_src, scene, runner),
                 "clocks": clocks}
         if cb:
             line["cpu_baseline"] = cb
@@ -580,6 +664,8 @@ def main():
     ap.add_argument("--workload", default="synthetic-256x256x64")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: how the ranks exchange their slabs of the field each step")
+    ap.add_argument("--rays-per-probe", type=int, default=64, choices=[16, 32, 64, 128, 256],
+                    help="BASELINE configs[4] sweeps 16-256 (the reference only defines 64); the demo / config-3 / glossy lines need 64")
     ap.add_argument("--no-demo", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--api-config3", action="store_true", help=argparse.SUPPRESS)

@@ -89,7 +89,7 @@ int main(int argc, char** argv) {
     unsigned long long sum = 0;
     for (uint32_t w : field) sum += (w & 1023u) + ((w >> 10) & 1023u) + ((w >> 20) & 1023u);
     printf("frames %d, requests last frame %lld, magicSize %d, field checksum %llu\n", lum.opaque_members->render.lumal.iFrame,
-           (long long)lum.opaque_members->render.lastRequestCount, lum.opaque_members->render.magicSize, sum);
+           (long long)lum.opaque_members->render.request_count(), lum.opaque_members->render.magicSize, sum);
     lum.cleanup();
     return 0;
 }

@@ -96,8 +96,7 @@ public:
     int device = 0;                                  // CUDA ordinal (env LUM_B200_DEVICE)
     int rays_per_probe = 64;                         // radiance.comp:37
     float reactiveness = 0.01f;                      // radiance.comp:28
-    int64_t lastRequestCount = 0;                    // size of the request list of the last frame
-    int64_t lastWorkgroupCount = 0;
+    int64_t request_count();                         // size of the request list of the last frame (asks the stage: one readback)
     bool worldDirty = true;                          // current_world differs from the device copy
 
     void init(const Lum::Settings& settings);

@@ -66,8 +66,15 @@ int lumcu_create(const LumcuDesc *desc, LumcuCtx **out);
 int lumcu_destroy(LumcuCtx *ctx);
 
 /* end_blockify + the world part of exec_copies: stagingWorld -> world image
- * (internal_render.cpp:1092-1103,1375-1476).  world_xyz: world_size x*y*z int16. */
+ * (internal_render.cpp:1092-1103,1375-1476).  world_xyz: world_size x*y*z int16.  The caller's buffer is consumed
+ * before the call returns (the reference copies synchronously too, renderer.cpp:135-138). */
 int lumcu_upload_world(LumcuCtx *ctx, const int16_t *world_xyz);
+/* The same without the wait, for a caller that keeps its world in page-locked memory (cudaHostAlloc /
+ * cudaHostRegister) -- the role of the reference's persistently mapped stagingWorld ring
+ * (internal_render.cpp:198-207, :1092-1097): the copy is queued behind the frame in flight and the call returns at
+ * once; the buffer must stay untouched until lumcu_wait_idle / a download / the next upload from it has returned.
+ * Pageable memory takes the synchronous path of lumcu_upload_world. */
+int lumcu_upload_world_async(LumcuCtx *ctx, const int16_t *world_xyz_pinned);
 
 /* updateBlockPalette (load_stuff.cpp:36-86) and the per-block brick copies of exec_copies
  * (internal_render.cpp:1402-1446): bricks [first_id, first_id+count) in BlockVoxels layout. */
@@ -83,7 +90,10 @@ int lumcu_set_requests(LumcuCtx *ctx, const int16_t *xyzw, int64_t n);
 
 /* Device-side restatement of the request-list builder (internal_render.cpp:1142-1169): probes
  * whose edge-clamped 3x3x3 neighbourhood of the uploaded world sums > 0, in z,y,x order, then the
- * special requests not already selected, in submission order.  out_count may be NULL. */
+ * special requests not already selected, in submission order.
+ * out_count == NULL: nothing waits for the GPU -- the count stays in device memory, the kernels of the following
+ * updates cut their dispatch down to it, and the host learns it when it first asks (lumcu_request_count,
+ * lumcu_download_requests, lumcu_slab_range, an instrumented update).  out_count != NULL: one 16-byte readback. */
 int lumcu_build_requests(LumcuCtx *ctx, const int16_t *special_xyzw, int32_t nspecial, int64_t *out_count);
 int lumcu_request_count(LumcuCtx *ctx, int64_t *out_count);
 int lumcu_download_requests(LumcuCtx *ctx, int16_t *out_xyzw, int64_t cap);
@@ -108,16 +118,21 @@ int lumcu_update_slab(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t sh
                       int32_t z_begin, int32_t z_end);
 
 /* ---- multi-GPU exchange over peer memory (one process per GPU; no reference counterpart) --------
- * Instead of "update the slab, then all-gather", the commit of a slab stores every new texel into the
- * field replica of EVERY rank through IPC-mapped peer pointers (NVLink P2P), bracketed by two flag
- * barriers: one launch sequence does the store_probe of radiance.comp:353 and the exchange.
- *   1. every rank: lumcu_ipc_export(ctx, blob)            (LUMCU_IPC_BYTES bytes)
+ * Instead of "update the shard, then all-gather", the store of radiance.comp:353 IS the exchange: the trace kernel
+ * stores each new texel into slot w (its workgroup) of the "inbox" of EVERY rank -- the rank's own staging array and
+ * the peers' through IPC-mapped pointers (NVLink P2P) -- straight from its last phase, so the transfer rides under
+ * the tracing.  A one-warp kernel then publishes "this rank has arrived" in every rank's flag array, and each rank's
+ * commit kernel waits for all flags (inside the kernel) and scatters the whole dispatch from its local inbox into its
+ * local field.  One barrier per frame, no collective call, nothing remote on the read side.  The inbox has two
+ * halves used alternately, so the next frame's stores cannot overtake a slower rank's commit.
+ *   1. every rank: lumcu_ipc_export(ctx, blob)            (LUMCU_IPC_BYTES bytes: inbox + flag array)
  *   2. exchange the blobs out of band (e.g. torch.distributed all_gather)
  *   3. every rank: lumcu_peers_open(ctx, rank, nranks, blobs)   (nranks x LUMCU_IPC_BYTES bytes, rank order)
- *   4. per frame, every rank: lumcu_update_slab_exchange(ctx, seed, size, shift, z0, z1) with its slab
- * All ranks must hold the same world, request list and field; results are bit-identical to
- * lumcu_update on one GPU.  A rank that stops participating makes the others' barrier time out
- * (~20 s) and their next call fail with LUMCU_E_STATE instead of hanging. */
+ *   4. per frame, every rank: lumcu_update_shard_exchange(ctx, seed, size, shift), or
+ *      lumcu_update_slab_exchange(ctx, seed, size, shift, z0, z1) with its z-slab
+ * All ranks must hold the same world, request list, field and max_requests; results are bit-identical to
+ * lumcu_update on one GPU.  A rank that stops participating makes the others' wait time out (~20 s) and their next
+ * call fail with LUMCU_E_STATE instead of hanging. */
 #define LUMCU_IPC_BYTES 128
 #define LUMCU_MAX_PEERS 16
 int lumcu_ipc_export(LumcuCtx *ctx, uint8_t *blob);
@@ -171,6 +186,15 @@ int lumcu_download_world(LumcuCtx *ctx, int16_t *world_xyz);
  * host-side consumer).  field_xyz: world cells uint32. */
 int lumcu_upload_field(LumcuCtx *ctx, const uint32_t *field_xyz);
 int lumcu_download_field(LumcuCtx *ctx, uint32_t *field_xyz);
+/* Words [first, first + count) of the field into page-locked host memory, queued on the stage's stream; returns at
+ * once.  The data is there once a fence recorded after this call has been waited for (or after lumcu_wait_idle). */
+int lumcu_download_field_async(LumcuCtx *ctx, uint32_t *out_pinned, int64_t first, int64_t count);
+/* Frames in flight (the reference keeps fif = 2 frames in flight behind fences, al.cpp:315-317): lumcu_record_fence
+ * marks the point the stage's stream has reached in one of LUMCU_FENCES slots, lumcu_wait_fence blocks the host until
+ * the GPU has passed it.  Waiting on a slot that was never recorded returns at once. */
+#define LUMCU_FENCES 4
+int lumcu_record_fence(LumcuCtx *ctx, int32_t slot);
+int lumcu_wait_fence(LumcuCtx *ctx, int32_t slot);
 
 /* The 64-entry sphericalFibonacci table the kernel uses (radiance.comp:293-314, evaluated on the
  * host in f32 at create time).  out: rays_per_probe*3 floats. */

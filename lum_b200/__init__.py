@@ -44,6 +44,7 @@ SYMBOLS = {
     "lumcu_create": (C.c_int, [C.POINTER(LumcuDesc), C.POINTER(_P)]),
     "lumcu_destroy": (C.c_int, [_P]),
     "lumcu_upload_world": (C.c_int, [_P, _P]),
+    "lumcu_upload_world_async": (C.c_int, [_P, _P]),
     "lumcu_upload_bricks": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "lumcu_upload_materials": (C.c_int, [_P, _P]),
     "lumcu_set_requests": (C.c_int, [_P, _P, C.c_int64]),
@@ -70,6 +71,9 @@ SYMBOLS = {
     "lumcu_download_world": (C.c_int, [_P, _P]),
     "lumcu_upload_field": (C.c_int, [_P, _P]),
     "lumcu_download_field": (C.c_int, [_P, _P]),
+    "lumcu_download_field_async": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
+    "lumcu_record_fence": (C.c_int, [_P, C.c_int32]),
+    "lumcu_wait_fence": (C.c_int, [_P, C.c_int32]),
     "lumcu_direction_table": (C.c_int, [_P, _P]),
     "lumcu_set_debug": (C.c_int, [_P, C.c_int32]),
     "lumcu_debug_extent": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -147,6 +151,11 @@ class RadianceStage:
         assert w.size == self.cells
         self._ck(self.lib.lumcu_upload_world(self.ctx, _ptr(w)))
 
+    def upload_world_async(self, world_pinned):
+        """world_pinned: an int16 array in page-locked memory that stays untouched until the stage is next synchronised."""
+        assert world_pinned.dtype == np.int16 and world_pinned.size == self.cells and world_pinned.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.lumcu_upload_world_async(self.ctx, _ptr(world_pinned)))
+
     def upload_bricks(self, first_id, bricks):
         b = np.ascontiguousarray(bricks, np.uint8).reshape(-1, 4096)
         self._ck(self.lib.lumcu_upload_bricks(self.ctx, int(first_id), b.shape[0], _ptr(b)))
@@ -165,11 +174,12 @@ class RadianceStage:
         r = np.ascontiguousarray(requests, np.int16).reshape(-1, 4)
         self._ck(self.lib.lumcu_set_requests(self.ctx, _ptr(r), r.shape[0]))
 
-    def build_requests(self, special=None):
+    def build_requests(self, special=None, sync=True):
+        """sync=False: nothing waits for the GPU; the count stays on the device (request_count() fetches it)."""
         sp = None if special is None else np.ascontiguousarray(special, np.int16).reshape(-1, 4)
         n = C.c_int64()
-        self._ck(self.lib.lumcu_build_requests(self.ctx, _ptr(sp), 0 if sp is None else sp.shape[0], C.byref(n)))
-        return n.value
+        self._ck(self.lib.lumcu_build_requests(self.ctx, _ptr(sp), 0 if sp is None else sp.shape[0], C.byref(n) if sync else None))
+        return n.value if sync else None
 
     # -- the hot path ---------------------------------------------------------------------
     def update(self, time_seed, size=1, shift=0):
@@ -287,6 +297,17 @@ class RadianceStage:
             out = np.empty(self.cells, np.uint32)
         self._ck(self.lib.lumcu_download_field(self.ctx, _ptr(out)))
         return out
+
+    def download_field_async(self, out_pinned, first=0, count=None):
+        count = self.cells - first if count is None else count
+        assert out_pinned.dtype == np.uint32 and out_pinned.size >= count
+        self._ck(self.lib.lumcu_download_field_async(self.ctx, _ptr(out_pinned), int(first), int(count)))
+
+    def record_fence(self, slot):
+        self._ck(self.lib.lumcu_record_fence(self.ctx, int(slot)))
+
+    def wait_fence(self, slot):
+        self._ck(self.lib.lumcu_wait_fence(self.ctx, int(slot)))
 
     def direction_table(self):
         out = np.zeros((self.rays, 3), np.float32)

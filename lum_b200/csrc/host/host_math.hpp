@@ -57,41 +57,47 @@ inline dmat4 model_transform(const quat& rot, const vec3& shift) {
     return m;
 }
 
-// mat4(inverse(m)): adjugate over determinant in double, each entry rounded to float; out is
-// column-major.
+// mat4(inverse(m)) as internal_render.cpp:1510 gets it from glm, each entry rounded to float; out is column-major.
 inline void inverse_to_float(const dmat4& a, float out[16]) {
-    const double s0 = a[0][0] * a[1][1] - a[1][0] * a[0][1];
-    const double s1 = a[0][0] * a[1][2] - a[1][0] * a[0][2];
-    const double s2 = a[0][0] * a[1][3] - a[1][0] * a[0][3];
-    const double s3 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
-    const double s4 = a[0][1] * a[1][3] - a[1][1] * a[0][3];
-    const double s5 = a[0][2] * a[1][3] - a[1][2] * a[0][3];
-    const double c5 = a[2][2] * a[3][3] - a[3][2] * a[2][3];
-    const double c4 = a[2][1] * a[3][3] - a[3][1] * a[2][3];
-    const double c3 = a[2][1] * a[3][2] - a[3][1] * a[2][2];
-    const double c2 = a[2][0] * a[3][3] - a[3][0] * a[2][3];
-    const double c1 = a[2][0] * a[3][2] - a[3][0] * a[2][2];
-    const double c0 = a[2][0] * a[3][1] - a[3][0] * a[2][1];
-    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-    const double id = 1.0 / det;
-    double b[4][4];
-    b[0][0] = ( a[1][1] * c5 - a[1][2] * c4 + a[1][3] * c3) * id;
-    b[0][1] = (-a[0][1] * c5 + a[0][2] * c4 - a[0][3] * c3) * id;
-    b[0][2] = ( a[3][1] * s5 - a[3][2] * s4 + a[3][3] * s3) * id;
-    b[0][3] = (-a[2][1] * s5 + a[2][2] * s4 - a[2][3] * s3) * id;
-    b[1][0] = (-a[1][0] * c5 + a[1][2] * c2 - a[1][3] * c1) * id;
-    b[1][1] = ( a[0][0] * c5 - a[0][2] * c2 + a[0][3] * c1) * id;
-    b[1][2] = (-a[3][0] * s5 + a[3][2] * s2 - a[3][3] * s1) * id;
-    b[1][3] = ( a[2][0] * s5 - a[2][2] * s2 + a[2][3] * s1) * id;
-    b[2][0] = ( a[1][0] * c4 - a[1][1] * c2 + a[1][3] * c0) * id;
-    b[2][1] = (-a[0][0] * c4 + a[0][1] * c2 - a[0][3] * c0) * id;
-    b[2][2] = ( a[3][0] * s4 - a[3][1] * s2 + a[3][3] * s0) * id;
-    b[2][3] = (-a[2][0] * s4 + a[2][1] * s2 - a[2][3] * s0) * id;
-    b[3][0] = (-a[1][0] * c3 + a[1][1] * c1 - a[1][2] * c0) * id;
-    b[3][1] = ( a[0][0] * c3 - a[0][1] * c1 + a[0][2] * c0) * id;
-    b[3][2] = (-a[3][0] * s3 + a[3][1] * s1 - a[3][2] * s0) * id;
-    b[3][3] = ( a[2][0] * s3 - a[2][1] * s1 + a[2][2] * s0) * id;
-    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) out[4 * c + r] = (float)b[c][r];
+    // glm::inverse(dmat4) as the vendored glm computes it (external/lum-al/external/glm/glm/detail/func_matrix.inl:388-447,
+    // compute_inverse<4,4>): the eighteen 2x2 sub-determinants, cofactor columns signed by a multiplication with +-1
+    // (which is where its -0.0 entries come from), the determinant as the dot of the first row, every entry times
+    // 1/det.  m[col][row].
+    const dmat4& m = a;
+    const double Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3];
+    const double Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
+    const double Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+    const double Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
+    const double Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3];
+    const double Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    const double Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2];
+    const double Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2];
+    const double Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    const double Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
+    const double Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3];
+    const double Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    const double Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2];
+    const double Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2];
+    const double Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+    const double Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+    const double Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1];
+    const double Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+    const double Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+    const double Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+    const double Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+    const double Vec0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]}, Vec1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+    const double Vec2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]}, Vec3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+    const double SignA[4] = {+1.0, -1.0, +1.0, -1.0}, SignB[4] = {-1.0, +1.0, -1.0, +1.0};
+    double inv[4][4];
+    for (int k = 0; k < 4; k++) {
+        inv[0][k] = ((Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k]) * SignA[k];
+        inv[1][k] = ((Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k]) * SignB[k];
+        inv[2][k] = ((Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k]) * SignA[k];
+        inv[3][k] = ((Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k]) * SignB[k];
+    }
+    const double Dot1 = (m[0][0] * inv[0][0] + m[0][1] * inv[1][0]) + (m[0][2] * inv[2][0] + m[0][3] * inv[3][0]);
+    const double OneOverDeterminant = 1.0 / Dot1;
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) out[4 * c + r] = (float)(inv[c][r] * OneOverDeterminant);
 }
 
 // right-handed look-at view matrix

@@ -132,7 +132,7 @@ void lum_b200_set_radiance_controller(LumRenderer instance, bool enabled, int ma
 }
 int lum_b200_get_magic_size(const LumRenderer instance) { return IR(instance).magicSize; }
 void lum_b200_set_radiance_time_override(LumRenderer instance, float ms) { IR(instance).radianceTimeOverride = ms; }
-long long lum_b200_get_request_count(const LumRenderer instance) { return IR(instance).lastRequestCount; }
+long long lum_b200_get_request_count(const LumRenderer instance) { return IR(instance).request_count(); }
 int lum_b200_get_frame_index(const LumRenderer instance) { return IR(instance).lumal.iFrame; }
 void lum_b200_download_radiance_field(LumRenderer instance, uint32_t* words) { IR(instance).download_radiance_field(words); }
 void lum_b200_upload_radiance_field(LumRenderer instance, const uint32_t* words) { IR(instance).upload_radiance_field(words); }

@@ -287,9 +287,9 @@ void LumInternalRenderer::update_radiance() {                            // :112
     for (const auto& u : specialRadianceUpdatesWide) { sp.push_back(u.x); sp.push_back(u.y); sp.push_back(u.z); sp.push_back(u.w); }
     specialRadianceUpdates.clear();
     specialRadianceUpdatesWide.clear();
-    int64_t n = 0;
-    check(lumcu_build_requests(stage, sp.empty() ? nullptr : sp.data(), (int32_t)(sp.size() / 4), &n), "lumcu_build_requests");
-    lastRequestCount = n;
+    // (no count comes back: the frame is queued without waiting for the GPU, as the reference records its command
+    // buffer; request_count() asks the stage when somebody wants the number)
+    check(lumcu_build_requests(stage, sp.empty() ? nullptr : sp.data(), (int32_t)(sp.size() / 4), nullptr), "lumcu_build_requests");
     // controller (:1190-1201)
     if (radianceControllerEnabled) {
         if (timeTakenByRadiance < 1.8f) magicSize--;
@@ -298,8 +298,13 @@ void LumInternalRenderer::update_radiance() {                            // :112
     magicSize = magicSize < 1 ? 1 : magicSize;
     magicSize = magicSize > 10 ? 10 : magicSize;
     // push constants {iFrame, 0, magicSize, iFrame % magicSize}; dispatch N / magicSize workgroups (:1202-1206)
-    lastWorkgroupCount = n / magicSize;
     check(lumcu_update(stage, lumal.iFrame, magicSize, lumal.iFrame % magicSize), "lumcu_update");
+}
+
+int64_t LumInternalRenderer::request_count() {
+    int64_t n = 0;
+    check(lumcu_request_count(stage, &n), "lumcu_request_count");
+    return n;
 }
 
 void LumInternalRenderer::end_frame() {                                  // :2081-2180, al.cpp:385-468

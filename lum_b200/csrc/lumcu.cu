@@ -82,6 +82,7 @@ struct LumcuCtx {
     cudaStream_t copy_stream = nullptr;    // uploads from caller-pinned memory (no staging copy)
     cudaEvent_t ev_compute = nullptr, ev_copy = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t fences[LUMCU_FENCES] = {};  // lumcu_record_fence / lumcu_wait_fence (created on first use)
     bool timed = false, profiling = false, ktimed = false;
 
     int16_t *d_world = nullptr;
@@ -96,8 +97,10 @@ struct LumcuCtx {
     std::vector<float> h_table;
     float sun[3] = {0, 0, 0};
 
-    long long nreq = 0;          // current request count
+    long long nreq = 0;          // current request count -- an upper bound while count_on_device
     long long nsorted = 0;       // leading requests known to be z-sorted
+    bool count_on_device = false;   // the list was built without a host sync: the true count is *d_total (+ d_nbuilt),
+                                    // the kernels cut their dispatch down to it, and the host learns it when asked
     bool have_world = false, have_bricks = false, have_materials = false;
     int sm_count = 148;          // cudaDevAttrMultiProcessorCount (grid sizing of the grid-stride kernels)
     int pool_threads = 128;      // tuning knobs (env LUMCU_POOL_THREADS / LUMCU_CARVEOUT, read at create)
@@ -112,7 +115,7 @@ struct LumcuCtx {
     uint8_t *d_flags = nullptr;
     uint32_t *d_block_counts = nullptr;
     unsigned long long *d_block_offsets = nullptr;
-    unsigned long long *d_total = nullptr;
+    unsigned long long *d_total = nullptr;      // [0] = requests in the list, [1] = of which built by the 3x3x3 rule (z-sorted)
     short4 *d_special = nullptr;
     long long special_cap = 0;
     long long *d_bounds = nullptr;
@@ -139,11 +142,11 @@ struct LumcuCtx {
     // peer exchange (lumcu_peers_open)
     bool have_peers = false;
     int peer_rank = 0, peer_n = 1;
-    PeerFields peer_fields{};
+    PeerWords peer_inbox[2]{};             // [parity]: that half of every rank's staged[] (own included)
     PeerFlags peer_flags{};
     void *peer_opened[2 * MAX_PEERS] = {};
     int n_peer_opened = 0;
-    unsigned *d_sync_flags = nullptr;      // [2][MAX_PEERS] epochs written by the peers
+    unsigned *d_sync_flags = nullptr;      // [MAX_PEERS] epoch each rank last arrived at (written by the peers)
     unsigned *h_status = nullptr;          // pinned + mapped: barrier timeout flag
     unsigned *d_status = nullptr;
     unsigned epoch = 0;
@@ -223,7 +226,9 @@ int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, lo
 
 template <bool DEBUG>
 int launch_update_R(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
-    dim3 grid((unsigned)nwg);
+    // one CTA per workgroup up to a full machine of resident CTAs (32 per SM), striding beyond: the grid of a small
+    // dispatch does not depend on the request count, which may still be on the device (and lets a CUDA graph replay it)
+    dim3 grid((unsigned)std::min<long long>(nwg, (long long)c->sm_count * 32));
     switch (c->R) {
         case 16: radiance_update_wg_kernel<16, DEBUG><<<grid, 16, 0, c->stream>>>(sv, a); break;
         case 32: radiance_update_wg_kernel<32, DEBUG><<<grid, 32, 0, c->stream>>>(sv, a); break;
@@ -277,13 +282,36 @@ long long il_count(long long total, const Interleave &il) {
     return (full / il.n) * il.chunk + ((full % il.n) > il.rank ? il.chunk : 0) + ((full % il.n) == il.rank ? rem : 0);
 }
 
+// The request count as the host needs it for launch sizes: exact, or (count_on_device) an upper bound.
+const unsigned long long *count_ptr(const LumcuCtx *c) { return c->count_on_device ? c->d_total : nullptr; }
+
+// Learn the device-side count (one 16-byte readback + sync); every entry point that needs exact numbers calls this.
+int resolve_count(LumcuCtx *c) {
+    if (!c->count_on_device) return 0;
+    unsigned long long t[2] = {0, 0};
+    CU(cudaMemcpyAsync(t, c->d_total, sizeof t, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->count_on_device = false;
+    if ((long long)t[0] > c->max_requests) {
+        c->nreq = 0; c->nsorted = 0;
+        return fail(LUMCU_E_ARG, "request list (%llu) exceeds max_requests %lld", t[0], c->max_requests);
+    }
+    c->nreq = (long long)t[0];
+    c->nsorted = (long long)t[1];
+    return 0;
+}
+
+uint32_t *staged_half(LumcuCtx *c, int parity) { return c->d_staged + (size_t)parity * (size_t)c->max_requests; }
+
+// xw.flags != null: a multi-GPU frame -- the staged half is this rank's inbox and the kernel waits for every rank's arrival
 int commit_local(LumcuCtx *c, int size, int shift, long long wg_begin, long long wg_end, int z_begin, int z_end,
-                 Interleave il = Interleave{IL_CHUNK, 0, 1}) {
+                 Interleave il = Interleave{IL_CHUNK, 0, 1}, int parity = 0, ExchangeWait xw = ExchangeWait{}) {
     const long long nwg = il_count(wg_end - wg_begin, il);
     if (nwg <= 0) return 0;
     const int ct = 256;
     commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
-        c->d_field, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il);
+        c->d_field, staged_half(c, parity), c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il,
+        count_ptr(c), xw);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -292,7 +320,8 @@ int commit_local(LumcuCtx *c, int size, int shift, long long wg_begin, long long
 // second_pass: this launch continues a frame another do_update() started (the special tail of a slab update): the
 // instrumented totals keep accumulating and the debug range stays the first pass's.
 int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begin, long long wg_end,
-              int z_begin, int z_end, bool commit = true, Interleave il = Interleave{IL_CHUNK, 0, 1}, bool second_pass = false) {
+              int z_begin, int z_end, bool commit = true, Interleave il = Interleave{IL_CHUNK, 0, 1}, bool second_pass = false,
+              const PeerWords *inbox = nullptr, int parity = 0) {
     if (!c->have_world || !c->have_bricks || !c->have_materials)
         return fail(LUMCU_E_STATE, "lumcu_update before world/bricks/materials were uploaded");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
@@ -307,7 +336,9 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         UpdateArgs a{};
         a.requests = c->d_requests;
         a.dir_table = c->d_table;
-        a.staged = c->d_staged;
+        a.staged = staged_half(c, parity);
+        if (inbox) a.inbox = *inbox;
+        a.nreq_dev = count_ptr(c);
         a.wg_begin = wg_begin; a.wg_end = wg_end;
         a.il_chunk = il.chunk; a.il_rank = il.rank; a.il_n = il.n;
         a.time_seed = time_seed; a.size = size; a.shift = shift;
@@ -319,6 +350,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         const bool unfiltered = z_begin <= -32768 && z_end >= 32768;
         const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && nwg * c->R >= (1ll << 23)));
         if (c->debug_flags) {
+            if (c->count_on_device) return fail(LUMCU_E_STATE, "instrumented update with an unresolved request count");
             if (int rc = ensure_debug(c)) return rc;
             a.dbg_pre_blend = (c->debug_flags & LUMCU_DEBUG_PRE_BLEND) ? c->d_pre_blend : nullptr;
             a.dbg_samples = (c->debug_flags & LUMCU_DEBUG_RAYS) ? c->d_ray_samples : nullptr;
@@ -338,29 +370,22 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             if (c->profiling) { CU(cudaEventRecord(c->ev_k1, c->stream)); c->ktimed = true; }
         }
         if (commit)
-            if (int rc = commit_local(c, size, shift, wg_begin, wg_end, z_begin, z_end, il)) return rc;
+            if (int rc = commit_local(c, size, shift, wg_begin, wg_end, z_begin, z_end, il, parity)) return rc;
     }
     return 0;
 }
 
-int commit_to_peers(LumcuCtx *c, int size, int shift, long long wg_begin, long long wg_end, int z_begin, int z_end,
-                    Interleave il = Interleave{IL_CHUNK, 0, 1}) {
-    const long long nwg = il_count(wg_end - wg_begin, il);
-    if (nwg <= 0) return 0;
-    const int ct = 256;
-    commit_peers_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
-        c->peer_fields, c->d_staged, c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il);
+constexpr long long PEER_TIMEOUT_CYCLES = 40000000000ll;      // ~20 s at 2 GHz: a rank that died must not hang the others' GPUs
+
+int arrive(LumcuCtx *c) {
+    arrive_kernel<<<1, 32, 0, c->stream>>>(c->peer_flags, c->epoch);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-int peer_barrier(LumcuCtx *c, int phase) {
-    // ~20 s at 2 GHz: a rank that died must not hang the others' GPUs
-    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(c->peer_flags, phase, c->epoch, 40000000000ll, c->d_status);
-    c->launches++;
-    CU(cudaGetLastError());
-    return 0;
+ExchangeWait exchange_wait(LumcuCtx *c) {
+    return ExchangeWait{c->d_sync_flags, c->peer_n, c->epoch, PEER_TIMEOUT_CYCLES, c->d_status};
 }
 
 }  // namespace
@@ -415,7 +440,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaMalloc(&c->d_mat4, 256 * sizeof(float4)));
     CUB(cudaMalloc(&c->d_field, (size_t)c->cells * sizeof(uint32_t)));
     CUB(cudaMalloc(&c->d_requests, (size_t)c->max_requests * sizeof(short4)));
-    CUB(cudaMalloc(&c->d_staged, (size_t)c->max_requests * sizeof(uint32_t)));
+    CUB(cudaMalloc(&c->d_staged, 2 * (size_t)c->max_requests * sizeof(uint32_t)));   // two halves: the exchange alternates
     CUB(cudaMalloc(&c->d_table, (size_t)R * 3 * sizeof(float)));
     CUB(cudaMemsetAsync(c->d_world, 0, (size_t)c->cells * sizeof(int16_t), c->stream));
     CUB(cudaMemsetAsync(c->d_bricks, 0, (size_t)d->palette_capacity * 4096, c->stream));
@@ -454,6 +479,7 @@ int lumcu_destroy(LumcuCtx *c) {
     for (auto &m : c->models) cudaFree(m.d_vox);
     cudaFree(c->d_pre_blend); cudaFree(c->d_ray_samples); cudaFree(c->d_ray_hits); cudaFree(c->d_totals);
     c->stage_world.release(); c->stage_req.release(); c->stage_misc.release(); c->stage_pairs.release();
+    for (auto &f : c->fences) if (f) cudaEventDestroy(f);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->ev_k0) cudaEventDestroy(c->ev_k0);
@@ -466,7 +492,7 @@ int lumcu_destroy(LumcuCtx *c) {
     return 0;
 }
 
-static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, size_t bytes) {
+static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, size_t bytes, bool wait = true) {
     // Caller buffer already page-locked (cudaHostAlloc / cudaHostRegister): copy straight from it on
     // the copy stream -- ordered after the work already queued (the kernels still reading dst) and
     // before whatever is queued next -- and return once the copy itself is done, so the buffer is
@@ -478,7 +504,7 @@ static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, s
         CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->ev_copy, c->copy_stream));
         CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-        CU(cudaEventSynchronize(c->ev_copy));
+        if (wait) CU(cudaEventSynchronize(c->ev_copy));      // (!wait: the caller keeps the buffer untouched, lumcu_upload_world_async)
         return 0;
     }
     cudaGetLastError();   // cudaPointerGetAttributes on plain pageable memory may leave an error state on old drivers
@@ -494,6 +520,15 @@ int lumcu_upload_world(LumcuCtx *c, const int16_t *world) {
     if (int rc = use(c)) return rc;
     if (!world) return fail(LUMCU_E_ARG, "null world");
     if (int rc = staged_upload(c, c->stage_world, c->d_world, world, (size_t)c->cells * sizeof(int16_t))) return rc;
+    c->have_world = true;
+    c->world_dirty = true;
+    return 0;
+}
+
+int lumcu_upload_world_async(LumcuCtx *c, const int16_t *world) {
+    if (int rc = use(c)) return rc;
+    if (!world) return fail(LUMCU_E_ARG, "null world");
+    if (int rc = staged_upload(c, c->stage_world, c->d_world, world, (size_t)c->cells * sizeof(int16_t), false)) return rc;
     c->have_world = true;
     c->world_dirty = true;
     return 0;
@@ -649,6 +684,7 @@ int lumcu_set_requests(LumcuCtx *c, const int16_t *xyzw, int64_t n) {
         c->nsorted = 0;
     }
     c->nreq = n;
+    c->count_on_device = false;
     c->req_version++;
     return 0;
 }
@@ -662,14 +698,13 @@ int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, 
         CU(cudaMalloc(&c->d_flags, (size_t)c->cells));
         CU(cudaMalloc(&c->d_block_counts, (size_t)nblocks * sizeof(uint32_t)));
         CU(cudaMalloc(&c->d_block_offsets, (size_t)nblocks * sizeof(unsigned long long)));
-        CU(cudaMalloc(&c->d_total, sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->d_total, 2 * sizeof(unsigned long long)));
     }
     build_count_kernel<<<(unsigned)nblocks, BUILD_THREADS, 0, c->stream>>>(c->d_world, c->wx, c->wy, c->wz, c->d_flags, c->d_block_counts);
     build_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_block_counts, c->d_block_offsets, nblocks, c->d_total);
     build_scatter_kernel<<<(unsigned)nblocks, BUILD_THREADS, 0, c->stream>>>(c->d_flags, c->d_block_offsets, c->wx, c->wy, c->wz, c->d_requests, c->max_requests);
     c->launches += 3;
     CU(cudaGetLastError());
-    unsigned long long nbuilt = 0, total = 0;
     if (nspecial > 0) {
         if (c->special_cap < nspecial) {
             cudaFree(c->d_special); c->d_special = nullptr; c->special_cap = 0;
@@ -677,31 +712,33 @@ int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, 
             c->special_cap = nspecial;
         }
         if (int rc = staged_upload(c, c->stage_misc, c->d_special, special, (size_t)nspecial * sizeof(short4))) return rc;
-        CU(cudaMemcpyAsync(&nbuilt, c->d_total, sizeof nbuilt, cudaMemcpyDeviceToHost, c->stream));
         build_specials_kernel<<<1, 1024, 0, c->stream>>>(c->d_flags, c->wx, c->wy, c->wz, c->d_special, nspecial, c->d_requests, c->d_total, c->max_requests);
         c->launches++;
         CU(cudaGetLastError());
     }
-    CU(cudaMemcpyAsync(&total, c->d_total, sizeof total, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (nspecial == 0) nbuilt = total;
-    if ((long long)total > c->max_requests)
-        return fail(LUMCU_E_ARG, "request list (%llu) exceeds max_requests %lld", total, c->max_requests);
-    c->nreq = (long long)total;
+    // The count stays on the device: the kernels of the frame cut their dispatch down to it, and nothing here waits
+    // for the GPU.  Until somebody asks (out_count, lumcu_request_count, ...) the host works with an upper bound.
+    c->count_on_device = true;
+    c->nreq = std::min<long long>(c->max_requests, c->cells + nspecial);
+    c->nsorted = 0;
     c->req_version++;
-    c->nsorted = (long long)nbuilt;
-    if (out_count) *out_count = (int64_t)total;
+    if (out_count) {
+        if (int rc = resolve_count(c)) return rc;
+        *out_count = (int64_t)c->nreq;
+    }
     return 0;
 }
 
 int lumcu_request_count(LumcuCtx *c, int64_t *out) {
     if (!c || !out) return fail(LUMCU_E_ARG, "null argument");
+    if (c->count_on_device) { if (int rc = use(c)) return rc; if (int rc = resolve_count(c)) return rc; }
     *out = c->nreq;
     return 0;
 }
 
 int lumcu_download_requests(LumcuCtx *c, int16_t *out, int64_t cap) {
     if (int rc = use(c)) return rc;
+    if (int rc = resolve_count(c)) return rc;
     if (!out || cap < c->nreq) return fail(LUMCU_E_ARG, "output too small for %lld requests", c->nreq);
     if (c->nreq > 0) CU(cudaMemcpyAsync(out, c->d_requests, (size_t)c->nreq * sizeof(short4), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -711,6 +748,7 @@ int lumcu_download_requests(LumcuCtx *c, int16_t *out, int64_t cap) {
 int lumcu_update(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift) {
     if (int rc = use(c)) return rc;
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
+    if (c->debug_flags) if (int rc = resolve_count(c)) return rc;      // the debug buffers are sized and read by exact counts
     CU(cudaEventRecord(c->ev_begin, c->stream));
     if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768)) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
@@ -720,6 +758,7 @@ int lumcu_update(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift) {
 
 int lumcu_update_range(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int64_t wg_begin, int64_t wg_end) {
     if (int rc = use(c)) return rc;
+    if (int rc = resolve_count(c)) return rc;
     CU(cudaEventRecord(c->ev_begin, c->stream));
     if (int rc = do_update(c, time_seed, size, shift, wg_begin, wg_end, -32768, 32768)) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
@@ -737,6 +776,7 @@ int lumcu_slab_range(LumcuCtx *c, int32_t size, int32_t shift, int32_t z_begin, 
     if (int rc = use(c)) return rc;
     if (size < 1 || shift < 0 || shift >= size || !wg_begin || !wg_end || z_begin > z_end)
         return fail(LUMCU_E_ARG, "bad slab arguments");
+    if (int rc = resolve_count(c)) return rc;
     // request coordinates are int16: anything outside means "unbounded" (slab_bound_kernel's predecessor of the
     // first workgroup is z = -32768, which must compare below every bound that can select something)
     z_begin = std::min(std::max(z_begin, -32767), 32768);
@@ -789,15 +829,15 @@ int lumcu_ipc_export(LumcuCtx *c, uint8_t *handle) {
     if (int rc = use(c)) return rc;
     if (!handle) return fail(LUMCU_E_ARG, "null argument");
     if (!c->d_sync_flags) {
-        CU(cudaMalloc(&c->d_sync_flags, 2 * MAX_PEERS * sizeof(unsigned)));
-        CU(cudaMemset(c->d_sync_flags, 0, 2 * MAX_PEERS * sizeof(unsigned)));
+        CU(cudaMalloc(&c->d_sync_flags, MAX_PEERS * sizeof(unsigned)));
+        CU(cudaMemset(c->d_sync_flags, 0, MAX_PEERS * sizeof(unsigned)));
         CU(cudaHostAlloc(&c->h_status, sizeof(unsigned), cudaHostAllocMapped));
         *c->h_status = 0;
         CU(cudaHostGetDevicePointer(&c->d_status, c->h_status, 0));
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, c->d_field));
+    CU(cudaIpcGetMemHandle(&h, c->d_staged));          // the inbox: both halves of staged[]
     memcpy(handle, &h, 64);
     CU(cudaIpcGetMemHandle(&h, c->d_sync_flags));
     memcpy(handle + 64, &h, 64);
@@ -822,11 +862,12 @@ int lumcu_peers_open(LumcuCtx *c, int32_t rank, int32_t nranks, const uint8_t *h
         return fail(LUMCU_E_ARG, "bad peer set (rank %d of %d, at most %d ranks)", rank, nranks, MAX_PEERS);
     if (!c->d_sync_flags) return fail(LUMCU_E_STATE, "lumcu_peers_open before lumcu_ipc_export");
     lumcu_peers_close(c);
-    c->peer_fields = PeerFields{};
+    c->peer_inbox[0] = PeerWords{}; c->peer_inbox[1] = PeerWords{};
     c->peer_flags = PeerFlags{};
+    // every rank must have created its stage with the same max_requests (the halves of staged[] are max_requests apart)
     for (int p = 0; p < nranks; p++) {
         if (p == rank) {
-            c->peer_fields.f[p] = c->d_field;
+            c->peer_inbox[0].p[p] = staged_half(c, 0); c->peer_inbox[1].p[p] = staged_half(c, 1);
             c->peer_flags.f[p] = c->d_sync_flags;
             continue;
         }
@@ -835,13 +876,13 @@ int lumcu_peers_open(LumcuCtx *c, int32_t rank, int32_t nranks, const uint8_t *h
         memcpy(&h, handles + 128 * p, 64);
         CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         c->peer_opened[c->n_peer_opened++] = ptr;
-        c->peer_fields.f[p] = (uint32_t *)ptr;
+        c->peer_inbox[0].p[p] = (uint32_t *)ptr; c->peer_inbox[1].p[p] = (uint32_t *)ptr + (size_t)c->max_requests;
         memcpy(&h, handles + 128 * p + 64, 64);
         CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         c->peer_opened[c->n_peer_opened++] = ptr;
         c->peer_flags.f[p] = (unsigned *)ptr;
     }
-    c->peer_fields.n = nranks;
+    c->peer_inbox[0].n = nranks; c->peer_inbox[1].n = nranks;
     c->peer_flags.n = nranks;
     c->peer_flags.rank = rank;
     c->peer_rank = rank; c->peer_n = nranks;
@@ -853,8 +894,35 @@ int lumcu_update_shard(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shi
     if (int rc = use(c)) return rc;
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LUMCU_E_ARG, "bad shard %d of %d", rank, nranks);
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
+    if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
     CU(cudaEventRecord(c->ev_begin, c->stream));
     if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, Interleave{IL_CHUNK, rank, nranks})) return rc;
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    c->timed = true;
+    return 0;
+}
+
+// One multi-GPU frame (epoch e, parity = e & 1):
+//   trace     this rank's workgroups; the new texels go straight into half `parity` of EVERY rank's staged[] (its
+//             inbox) from the kernel's last phase -- peer stores over NVLink, spread over the whole trace;
+//   arrive    a one-warp kernel: system fence, then e into every rank's flag array;
+//   commit    waits (inside the kernel) until every rank has arrived at e, then scatters the whole dispatch from the
+//             local inbox into the local field.  Nothing remote is read or written here.
+// One barrier per frame.  The next frame's trace reads only local memory (stream order suffices) and writes the other
+// half of the inboxes; a rank can be writing half p of a peer's inbox again (epoch e + 2) only after the barrier of
+// epoch e + 1, which that peer reaches after its commit of epoch e -- the last reader of half p -- in stream order.
+static int exchange_frame(LumcuCtx *c, int time_seed, int size, int shift, long long b, long long e, bool slab,
+                          int z_begin, int z_end, Interleave il) {
+    const long long nwg_all = c->nreq / size, tail = slab ? sorted_workgroups(c, size, shift) : nwg_all;
+    c->epoch++;
+    const int parity = (int)(c->epoch & 1u);
+    const PeerWords *inbox = &c->peer_inbox[parity];
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768, false, il, false, inbox, parity)) return rc;
+    if (slab && tail < nwg_all)      // unsorted tail (specials): every rank scans it, keeps its slab's probes
+        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false, Interleave{IL_CHUNK, 0, 1}, true, inbox, parity)) return rc;
+    if (int rc = arrive(c)) return rc;
+    if (int rc = commit_local(c, size, shift, 0, nwg_all, -32768, 32768, Interleave{IL_CHUNK, 0, 1}, parity, exchange_wait(c))) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;
@@ -865,17 +933,8 @@ int lumcu_update_shard_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, in
     if (!c->have_peers) return fail(LUMCU_E_STATE, "lumcu_update_shard_exchange before lumcu_peers_open");
     if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
-    const Interleave il{IL_CHUNK, c->peer_rank, c->peer_n};
-    const long long nwg_all = c->nreq / size;
-    c->epoch++;
-    CU(cudaEventRecord(c->ev_begin, c->stream));
-    if (int rc = do_update(c, time_seed, size, shift, 0, nwg_all, -32768, 32768, false, il)) return rc;
-    if (int rc = peer_barrier(c, 0)) return rc;             // every rank has finished reading its field
-    if (int rc = commit_to_peers(c, size, shift, 0, nwg_all, -32768, 32768, il)) return rc;
-    if (int rc = peer_barrier(c, 1)) return rc;             // every rank's texels have landed everywhere
-    CU(cudaEventRecord(c->ev_end, c->stream));
-    c->timed = true;
-    return 0;
+    if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
+    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, Interleave{IL_CHUNK, c->peer_rank, c->peer_n});
 }
 
 int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
@@ -883,21 +942,8 @@ int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int
     if (!c->have_peers) return fail(LUMCU_E_STATE, "lumcu_update_slab_exchange before lumcu_peers_open");
     if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
     int64_t b = 0, e = 0;
-    if (int rc = lumcu_slab_range(c, size, shift, z_begin, z_end, &b, &e)) return rc;
-    const long long nwg_all = c->nreq / size, tail = sorted_workgroups(c, size, shift);
-    c->epoch++;
-    CU(cudaEventRecord(c->ev_begin, c->stream));
-    if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768, false)) return rc;
-    if (tail < nwg_all)
-        if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false, Interleave{IL_CHUNK, 0, 1}, true)) return rc;
-    if (int rc = peer_barrier(c, 0)) return rc;             // every rank has finished reading its field
-    if (int rc = commit_to_peers(c, size, shift, b, e, -32768, 32768)) return rc;
-    if (tail < nwg_all)
-        if (int rc = commit_to_peers(c, size, shift, tail, nwg_all, z_begin, z_end)) return rc;
-    if (int rc = peer_barrier(c, 1)) return rc;             // every rank's texels have landed everywhere
-    CU(cudaEventRecord(c->ev_end, c->stream));
-    c->timed = true;
-    return 0;
+    if (int rc = lumcu_slab_range(c, size, shift, z_begin, z_end, &b, &e)) return rc;      // (resolves the request count)
+    return exchange_frame(c, time_seed, size, shift, b, e, true, z_begin, z_end, Interleave{IL_CHUNK, 0, 1});
 }
 
 int lumcu_shift(LumcuCtx *c, int32_t dx, int32_t dy, int32_t dz) {
@@ -923,6 +969,28 @@ int lumcu_download_field(LumcuCtx *c, uint32_t *f) {
     if (!f) return fail(LUMCU_E_ARG, "null field");
     CU(cudaMemcpyAsync(f, c->d_field, (size_t)c->cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lumcu_download_field_async(LumcuCtx *c, uint32_t *out, int64_t first, int64_t count) {
+    if (int rc = use(c)) return rc;
+    if (!out || first < 0 || count < 0 || first + count > c->cells) return fail(LUMCU_E_ARG, "bad field range [%lld, +%lld)", (long long)first, (long long)count);
+    if (count > 0) CU(cudaMemcpyAsync(out, c->d_field + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+int lumcu_record_fence(LumcuCtx *c, int32_t slot) {
+    if (int rc = use(c)) return rc;
+    if (slot < 0 || slot >= LUMCU_FENCES) return fail(LUMCU_E_ARG, "fence slot %d outside [0,%d)", slot, LUMCU_FENCES);
+    if (!c->fences[slot]) CU(cudaEventCreateWithFlags(&c->fences[slot], cudaEventDisableTiming));
+    CU(cudaEventRecord(c->fences[slot], c->stream));
+    return 0;
+}
+
+int lumcu_wait_fence(LumcuCtx *c, int32_t slot) {
+    if (int rc = use(c)) return rc;
+    if (slot < 0 || slot >= LUMCU_FENCES) return fail(LUMCU_E_ARG, "fence slot %d outside [0,%d)", slot, LUMCU_FENCES);
+    if (c->fences[slot]) CU(cudaEventSynchronize(c->fences[slot]));
     return 0;
 }
 

@@ -4,10 +4,20 @@
 
 namespace lumcu {
 
+// Multi-GPU exchange (one process per GPU, NVLink peer memory): the new texel of workgroup w is stored into slot w of
+// the "inbox" of EVERY rank -- the rank's own staged[] array and the peers' through IPC-mapped pointers -- straight
+// from the trace kernel's last phase, so the transfer rides under the tracing instead of following it.  n <= 1: only
+// UpdateArgs::staged is written.
+constexpr int MAX_PEERS = 16;
+struct PeerWords { uint32_t *p[MAX_PEERS]; int n; };
+
 struct UpdateArgs {
     const short4 *__restrict__ requests;   // x,y,z,w per request
     const float *__restrict__ dir_table;   // [R][3]
     uint32_t *__restrict__ staged;         // [nwg] packed texel per workgroup (committed afterwards)
+    PeerWords inbox;                       // n > 1: staged[] of every rank (own included), see above
+    const unsigned long long *__restrict__ nreq_dev;   // non-null: the request count lives on the device (a list
+                                           // built without a host sync); the dispatch is min(wg_end, *nreq_dev / size)
     float *__restrict__ dbg_pre_blend;     // [nwg][3] or null
     uint32_t *__restrict__ dbg_samples;    // [nwg*R] or null
     uint8_t *__restrict__ dbg_hits;        // [nwg*R] or null
@@ -31,6 +41,22 @@ __device__ __forceinline__ long long il_map(long long wg_begin, int il_chunk, in
     return wg_begin + (c * il_n + il_rank) * il_chunk + (i - c * il_chunk);
 }
 
+// last workgroup (exclusive) of this launch: the host's bound, cut down to the device-side request count if there is one
+__device__ __forceinline__ long long dispatch_end(const UpdateArgs &a) {
+    long long e = a.wg_end;
+    if (a.nreq_dev) { const long long n = (long long)(__ldg(a.nreq_dev) / (unsigned long long)a.size); e = n < e ? n : e; }
+    return e;
+}
+// a12's store, deferred: the packed texel of workgroup w goes to slot w of every rank's inbox
+__device__ __forceinline__ void stage_word(const UpdateArgs &a, long long w, uint32_t word) {
+    if (a.inbox.n > 1) {
+#pragma unroll 4
+        for (int p = 0; p < a.inbox.n; p++) a.inbox.p[p][w] = word;
+    } else {
+        a.staged[w] = word;
+    }
+}
+
 // One CTA = one workgroup of radiance.comp (radiance.comp:360-414): R threads, one ray each.
 // The subgroup reduction is the xor butterfly the oracle pins; _light[] lives in shared memory.
 template <int R, bool DEBUG>
@@ -39,16 +65,19 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
     constexpr int NSUB = R / SUB;
     __shared__ float sh_light[NSUB][3];
 
-    const long long w = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x);
-    if (w >= a.wg_end) return;                                   // uniform per CTA (tail of an interleaved shard)
+    // The grid is capped (a launch must not depend on a request count that only the device knows): CTAs stride.
+    const long long wg_end = dispatch_end(a);
     const int ray = threadIdx.x;
+    const bool valid = s.brick0_empty && !(__ldg(s.flags) & 1u);        // uniform
+    for (long long i = blockIdx.x;; i += gridDim.x) {
+    const long long w = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, i);
+    if (w >= wg_end) return;                                     // uniform per CTA (tail of an interleaved shard)
     const short4 rq = a.requests[w * (long long)a.size + a.shift];
-    if (rq.z < a.z_begin || rq.z >= a.z_end) return;          // uniform per CTA
+    if (rq.z < a.z_begin || rq.z >= a.z_end) continue;        // uniform per CTA
     const uint32_t gid_x = (uint32_t)(w * R + ray);
     const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
     const f3 sun = {a.sun_x, a.sun_y, a.sun_z};
 
-    const bool valid = s.brick0_empty && !(__ldg(s.flags) & 1u);        // uniform
     RayResult r = valid ? trace_probe_ray<true>(s, rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, sun)
                         : trace_probe_ray<false>(s, rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, sun);
 
@@ -95,7 +124,9 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
             const float t = a.reactiveness, omt = 1.0f - t;
             word = pack10(old.x * omt + fr * t, old.y * omt + fg * t, old.z * omt + fb * t);
         }
-        a.staged[w] = word;
+        stage_word(a, w, word);
+    }
+    __syncthreads();                                             // sh_light is reused by the next workgroup
     }
 }
 
@@ -296,7 +327,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     int (&sm_park)[3] = cta.park;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long wg0 = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x * PPC);   // il_chunk % PPC == 0
-    const long long left = a.wg_end - wg0;
+    const long long left = dispatch_end(a) - wg0;
     if (left <= 0) return;                                       // uniform per CTA (tail of an interleaved shard)
     const int nprobes = left < PPC ? (int)left : PPC;
     const int nrays = nprobes * R;
@@ -409,7 +440,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
             const float t = a.reactiveness, omt = 1.0f - t;
             word = pack10(old.x * omt + fr * t, old.y * omt + fg * t, old.z * omt + fb * t);
         }
-        a.staged[w] = word;
+        stage_word(a, w, word);
     }
 }
 
@@ -433,61 +464,57 @@ __global__ void validate_world_kernel(const int16_t *__restrict__ world, long lo
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flags, 1u);
 }
 
-// Deferred imageStore (radiance.comp:353): scatter the staged texels of workgroups
-// [wg_begin, wg_end) into the field once every read of the old field is done.
+// Barrier flags of the multi-GPU exchange: flags[r] of a rank holds the epoch rank r last arrived at (written by
+// rank r's arrive_kernel over NVLink, only ever growing).
+struct PeerFlags { unsigned *f[MAX_PEERS]; int n; int rank; };
+struct ExchangeWait {
+    const volatile unsigned *flags;        // this rank's flag array, or null: no exchange (single GPU)
+    int n;
+    unsigned epoch;
+    long long timeout_cycles;
+    volatile unsigned *status;             // set to 1 when a rank never arrived
+};
+
+// Deferred imageStore (radiance.comp:353): scatter the staged texels of workgroups [wg_begin, wg_end) into the field
+// once every read of the old field is done.  In a multi-GPU frame the staged array is this rank's inbox: every rank
+// (this one included) stored the texels of its own workgroups there during its trace kernel, and xw names the epoch
+// all of them must have arrived at before the inbox is complete -- thread 0 of each CTA waits for the flags (a rank
+// that never arrives trips the timeout instead of hanging the GPU), the commit itself is local.
 struct Interleave { int chunk, rank, n; };
 __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__restrict__ staged,
                               const short4 *__restrict__ requests, long long wg_begin, long long wg_end,
-                              int size, int shift, int wx, int wy, int wz, int z_begin, int z_end, Interleave il) {
+                              int size, int shift, int wx, int wy, int wz, int z_begin, int z_end, Interleave il,
+                              const unsigned long long *__restrict__ nreq_dev, ExchangeWait xw) {
+    if (xw.flags) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            for (int p = 0; p < xw.n; p++)
+                while ((int)(xw.flags[p] - xw.epoch) < 0) {
+                    __nanosleep(100);
+                    if (clock64() - t0 > xw.timeout_cycles) { *xw.status = 1u; break; }
+                }
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
+    if (nreq_dev) { const long long n = (long long)(*nreq_dev / (unsigned long long)size); wg_end = n < wg_end ? n : wg_end; }
     long long w = il_map(wg_begin, il.chunk, il.rank, il.n, (long long)blockIdx.x * blockDim.x + threadIdx.x);
     if (w >= wg_end) return;
     short4 rq = requests[w * (long long)size + shift];
     if (rq.z < z_begin || rq.z >= z_end) return;
     if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz)
-        field[rq.x + wx * (rq.y + wy * rq.z)] = staged[w];
+        field[rq.x + wx * (rq.y + wy * rq.z)] = __ldcv(staged + w);      // written by peers: not through a stale L1 line
 }
 
-// ---- multi-GPU exchange over peer memory (one process per GPU, NVLink P2P) -------------------
-// The commit of a rank's slab is also its part of the all-gather: every staged texel is stored
-// into the field replica of every rank (the local one and the peers' through IPC-mapped pointers),
-// bracketed by two flag barriers (peer_barrier_kernel) instead of a collective call.
-constexpr int MAX_PEERS = 16;
-struct PeerFields { uint32_t *f[MAX_PEERS]; int n; };
-struct PeerFlags { unsigned *f[MAX_PEERS]; int n; int rank; };
-
-__global__ void commit_peers_kernel(PeerFields pf, const uint32_t *__restrict__ staged,
-                                    const short4 *__restrict__ requests, long long wg_begin, long long wg_end,
-                                    int size, int shift, int wx, int wy, int wz, int z_begin, int z_end, Interleave il) {
-    long long w = il_map(wg_begin, il.chunk, il.rank, il.n, (long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (w >= wg_end) return;
-    short4 rq = requests[w * (long long)size + shift];
-    if (rq.z < z_begin || rq.z >= z_end) return;
-    if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz) {
-        const uint32_t word = staged[w];
-        const int cell = rq.x + wx * (rq.y + wy * rq.z);
-#pragma unroll 4
-        for (int p = 0; p < pf.n; p++) pf.f[p][cell] = word;
-    }
-}
-
-// Barrier across the ranks: lane p publishes `epoch` into slot [phase][my rank] of rank p's flag
-// array (after a system-scope fence, so everything this GPU wrote before -- the peer stores of the
-// commit -- is visible first) and then waits until rank p's epoch shows up in the local array.
-// Flags only grow, so no reset is needed.  A rank that never arrives trips the timeout (*status = 1)
-// instead of hanging the GPU.
-__global__ void peer_barrier_kernel(PeerFlags pf, int phase, unsigned epoch, long long timeout_cycles,
-                                    volatile unsigned *status) {
+// "This rank has finished tracing epoch `epoch`, and everything it stored into the other ranks' inboxes is visible":
+// runs right after the trace kernel on the same stream (its stores are complete when this starts; the system-scope
+// fence orders them before the flag for any observer), lane p publishes the epoch in rank p's flag array.
+__global__ void arrive_kernel(PeerFlags pf, unsigned epoch) {
     const int p = threadIdx.x;
+    __threadfence_system();
     if (p < pf.n) {
-        __threadfence_system();
-        volatile unsigned *dst = pf.f[p] + phase * MAX_PEERS + pf.rank;
+        volatile unsigned *dst = pf.f[p] + pf.rank;
         *dst = epoch;
-        volatile unsigned *src = pf.f[pf.rank] + phase * MAX_PEERS + p;
-        const long long t0 = clock64();
-        while ((int)(*src - epoch) < 0) {
-            __nanosleep(100);
-            if (clock64() - t0 > timeout_cycles) { *status = 1u; break; }
-        }
     }
     __threadfence_system();
 }
@@ -612,7 +639,7 @@ __global__ void build_scan_kernel(const uint32_t *__restrict__ block_counts, uns
         if (threadIdx.x == blockDim.x - 1) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (threadIdx.x == 0) { total[0] = carry; total[1] = carry; }    // [1]: the rule-built (z-sorted) prefix; specials only grow [0]
 }
 
 // pass 3: ordered scatter (z,y,x order == linear cell order)

@@ -398,3 +398,70 @@ def ref_glsl_glossy(scene: Scene, field, view, mat_norm, depth, frame=None):
                                      _p(v), C.c_int(w), C.c_int(h), _p(mn), _p(dp), _p(fr), _p(cov), _p(nf))
     assert rc == 0, rc
     return dict(frame=fr, covered=cov, fetches=nf)
+
+
+# ---- oracle/_ref: the reference's HOST-side C++ of the path, compiled in place (ref_host.cpp) ----
+_REF_HOST_PATH = os.path.join(_HERE, "_ref", "libref_host.so")
+_ref_host = None
+
+
+def ref_host_available() -> bool:
+    return os.path.exists(_REF_HOST_PATH)
+
+
+def _ref_host_lib():
+    global _ref_host
+    if _ref_host is None:
+        _ref_host = C.CDLL(_REF_HOST_PATH)
+        _ref_host.ref_host_place_model.restype = C.c_int
+        _ref_host.ref_host_blockify.restype = C.c_int
+        _ref_host.ref_host_build_requests.restype = C.c_longlong
+    return _ref_host
+
+
+def ref_host_place_model(rot_wxyz, shift, size, world_size):
+    """The reference's get_shift + blockify_mesh border + map_mesh arithmetic (internal_render.cpp:989-1013,
+    1030-1037, 1501-1510) -> a Placement like place_model()'s.  block_min/max come back as the extent of the cells
+    blockify_mesh actually allocated on an empty world."""
+    r = (C.c_float * 4)(*[float(v) for v in rot_wxyz])
+    s = (C.c_float * 3)(*[float(v) for v in shift])
+    z = (C.c_int32 * 3)(*[int(v) for v in size])
+    w = (C.c_int32 * 3)(*[int(v) for v in world_size])
+    out = Placement()
+    _ref_host_lib().ref_host_place_model(r, s, z, w, out.aabb_min, out.aabb_max, out.block_min, out.block_max,
+                                         out.map_shift, out.map_area, out.inverse_trans)
+    return out
+
+
+def ref_host_blockify(origin_world, static_count, models):
+    """The reference's start_blockify + blockify_mesh (internal_render.cpp:977-987, 1029-1076) per model in draw
+    order.  models: [(rot_wxyz, shift, size)].  -> (current_world, copy_src, copy_dst, queued_image_copies)."""
+    ow = np.ascontiguousarray(origin_world, np.int16)
+    wz, wy, wx = ow.shape
+    cur = np.empty_like(ow)
+    rot = np.ascontiguousarray([m[0] for m in models], np.float32).reshape(-1)
+    sh = np.ascontiguousarray([m[1] for m in models], np.float32).reshape(-1)
+    sz = np.ascontiguousarray([m[2] for m in models], np.int32).reshape(-1)
+    cap = ow.size
+    src = np.zeros(cap, np.int32); dst = np.zeros(cap, np.int32)
+    queued = C.c_int32()
+    n = _ref_host_lib().ref_host_blockify(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(ow), _p(cur), C.c_int(static_count),
+                                          C.c_int(len(models)), _p(rot), _p(sh), _p(sz), _p(src), _p(dst), C.c_int32(cap),
+                                          C.byref(queued))
+    return cur, src[:n].copy(), dst[:n].copy(), int(queued.value)
+
+
+def ref_host_build_requests(world, special=None):
+    """The reference's update_radiance list rule (internal_render.cpp:1132-1169).  Coordinates are i8vec4 there:
+    worlds up to 127 blocks per axis.  -> int16 [n,4] like build_requests()."""
+    world = np.ascontiguousarray(world, np.int16)
+    wz, wy, wx = world.shape
+    assert max(wx, wy, wz) <= 127
+    sp = None if special is None else np.ascontiguousarray(special, np.int8).reshape(-1, 4)
+    nsp = 0 if sp is None else sp.shape[0]
+    cap = world.size + nsp
+    out = np.zeros((cap, 4), np.int8)
+    n = _ref_host_lib().ref_host_build_requests(C.c_int(wx), C.c_int(wy), C.c_int(wz), _p(world), _p(sp), C.c_int(nsp),
+                                                _p(out), C.c_longlong(cap))
+    assert n >= 0
+    return out[:n].astype(np.int16)

@@ -4,8 +4,9 @@
  *
  * TEST INFRASTRUCTURE ONLY (see lum_oracle.h).  map.comp is PINNED against the reference's own
  * shader text executed on the CPU (oracle/_ref/libref_map_glsl.so, tests/test_ref_glsl.py);
- * placement / blockify / copies are PARITY UNPINNED: the reference has no tests or golden vectors
- * for them and its Vulkan host code (internal_render.cpp) does not compile from a few sources.
+ * placement / blockify are PINNED against the reference's own host C++ -- get_shift, blockify_mesh and
+ * map_mesh's arithmetic cut out of internal_render.cpp and compiled in place (oracle/_ref/libref_host.so,
+ * tests/test_ref_host.py, tests/golden/ref_host_golden.npz); the brick copies follow from blockify's pairs.
  * Each function follows the statement order of the reference text it cites (paths relative to
  * /root/reference).  Arithmetic rules: as lum_oracle.c (binary32/binary64 exactly as the reference
  * types them, one rounding per written operation, no FMA contraction).
@@ -34,41 +35,47 @@ static void quat_to_mat(const float q[4], float m[3][3]) {
     m[2][0] = 2.0f * (xz + wy);        m[2][1] = 2.0f * (yz - wx);        m[2][2] = 1.0f - 2.0f * (xx + yy);
 }
 
-/* inverse of the 4x4 [R|s; 0 0 0 1] in double by the adjugate (2x2 sub-determinants), rounded to
- * float per entry: mat4(inverse(transform)) (internal_render.cpp:1513).  a[col][row]. */
+/* mat4(inverse(transform)) (internal_render.cpp:1510): glm's double 4x4 inverse, each entry rounded to float.  a[col][row]. */
 static void inverse4(const double a[4][4], float out[16]) {
-    const double s0 = a[0][0] * a[1][1] - a[1][0] * a[0][1];
-    const double s1 = a[0][0] * a[1][2] - a[1][0] * a[0][2];
-    const double s2 = a[0][0] * a[1][3] - a[1][0] * a[0][3];
-    const double s3 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
-    const double s4 = a[0][1] * a[1][3] - a[1][1] * a[0][3];
-    const double s5 = a[0][2] * a[1][3] - a[1][2] * a[0][3];
-    const double c5 = a[2][2] * a[3][3] - a[3][2] * a[2][3];
-    const double c4 = a[2][1] * a[3][3] - a[3][1] * a[2][3];
-    const double c3 = a[2][1] * a[3][2] - a[3][1] * a[2][2];
-    const double c2 = a[2][0] * a[3][3] - a[3][0] * a[2][3];
-    const double c1 = a[2][0] * a[3][2] - a[3][0] * a[2][2];
-    const double c0 = a[2][0] * a[3][1] - a[3][0] * a[2][1];
-    const double det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-    const double id = 1.0 / det;
-    double b[4][4];
-    b[0][0] = ( a[1][1] * c5 - a[1][2] * c4 + a[1][3] * c3) * id;
-    b[0][1] = (-a[0][1] * c5 + a[0][2] * c4 - a[0][3] * c3) * id;
-    b[0][2] = ( a[3][1] * s5 - a[3][2] * s4 + a[3][3] * s3) * id;
-    b[0][3] = (-a[2][1] * s5 + a[2][2] * s4 - a[2][3] * s3) * id;
-    b[1][0] = (-a[1][0] * c5 + a[1][2] * c2 - a[1][3] * c1) * id;
-    b[1][1] = ( a[0][0] * c5 - a[0][2] * c2 + a[0][3] * c1) * id;
-    b[1][2] = (-a[3][0] * s5 + a[3][2] * s2 - a[3][3] * s1) * id;
-    b[1][3] = ( a[2][0] * s5 - a[2][2] * s2 + a[2][3] * s1) * id;
-    b[2][0] = ( a[1][0] * c4 - a[1][1] * c2 + a[1][3] * c0) * id;
-    b[2][1] = (-a[0][0] * c4 + a[0][1] * c2 - a[0][3] * c0) * id;
-    b[2][2] = ( a[3][0] * s4 - a[3][1] * s2 + a[3][3] * s0) * id;
-    b[2][3] = (-a[2][0] * s4 + a[2][1] * s2 - a[2][3] * s0) * id;
-    b[3][0] = (-a[1][0] * c3 + a[1][1] * c1 - a[1][2] * c0) * id;
-    b[3][1] = ( a[0][0] * c3 - a[0][1] * c1 + a[0][2] * c0) * id;
-    b[3][2] = (-a[3][0] * s3 + a[3][1] * s1 - a[3][2] * s0) * id;
-    b[3][3] = ( a[2][0] * s3 - a[2][1] * s1 + a[2][2] * s0) * id;
-    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) out[4 * c + r] = (float)b[c][r];
+    /* glm::inverse(dmat4) as the vendored glm computes it (external/lum-al/external/glm/glm/detail/func_matrix.inl:388-447,
+     * compute_inverse<4,4>): the eighteen 2x2 sub-determinants, cofactor columns signed by a multiplication with +-1
+     * (which is where its -0.0 entries come from), the determinant as the dot of the first row, every entry times
+     * 1/det.  m[col][row]. */
+    const double (*m)[4] = a;
+    const double Coef00 = m[2][2] * m[3][3] - m[3][2] * m[2][3];
+    const double Coef02 = m[1][2] * m[3][3] - m[3][2] * m[1][3];
+    const double Coef03 = m[1][2] * m[2][3] - m[2][2] * m[1][3];
+    const double Coef04 = m[2][1] * m[3][3] - m[3][1] * m[2][3];
+    const double Coef06 = m[1][1] * m[3][3] - m[3][1] * m[1][3];
+    const double Coef07 = m[1][1] * m[2][3] - m[2][1] * m[1][3];
+    const double Coef08 = m[2][1] * m[3][2] - m[3][1] * m[2][2];
+    const double Coef10 = m[1][1] * m[3][2] - m[3][1] * m[1][2];
+    const double Coef11 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    const double Coef12 = m[2][0] * m[3][3] - m[3][0] * m[2][3];
+    const double Coef14 = m[1][0] * m[3][3] - m[3][0] * m[1][3];
+    const double Coef15 = m[1][0] * m[2][3] - m[2][0] * m[1][3];
+    const double Coef16 = m[2][0] * m[3][2] - m[3][0] * m[2][2];
+    const double Coef18 = m[1][0] * m[3][2] - m[3][0] * m[1][2];
+    const double Coef19 = m[1][0] * m[2][2] - m[2][0] * m[1][2];
+    const double Coef20 = m[2][0] * m[3][1] - m[3][0] * m[2][1];
+    const double Coef22 = m[1][0] * m[3][1] - m[3][0] * m[1][1];
+    const double Coef23 = m[1][0] * m[2][1] - m[2][0] * m[1][1];
+    const double Fac0[4] = {Coef00, Coef00, Coef02, Coef03}, Fac1[4] = {Coef04, Coef04, Coef06, Coef07};
+    const double Fac2[4] = {Coef08, Coef08, Coef10, Coef11}, Fac3[4] = {Coef12, Coef12, Coef14, Coef15};
+    const double Fac4[4] = {Coef16, Coef16, Coef18, Coef19}, Fac5[4] = {Coef20, Coef20, Coef22, Coef23};
+    const double Vec0[4] = {m[1][0], m[0][0], m[0][0], m[0][0]}, Vec1[4] = {m[1][1], m[0][1], m[0][1], m[0][1]};
+    const double Vec2[4] = {m[1][2], m[0][2], m[0][2], m[0][2]}, Vec3[4] = {m[1][3], m[0][3], m[0][3], m[0][3]};
+    const double SignA[4] = {+1.0, -1.0, +1.0, -1.0}, SignB[4] = {-1.0, +1.0, -1.0, +1.0};
+    double inv[4][4];
+    for (int k = 0; k < 4; k++) {
+        inv[0][k] = ((Vec1[k] * Fac0[k] - Vec2[k] * Fac1[k]) + Vec3[k] * Fac2[k]) * SignA[k];
+        inv[1][k] = ((Vec0[k] * Fac0[k] - Vec2[k] * Fac3[k]) + Vec3[k] * Fac4[k]) * SignB[k];
+        inv[2][k] = ((Vec0[k] * Fac1[k] - Vec1[k] * Fac3[k]) + Vec3[k] * Fac5[k]) * SignA[k];
+        inv[3][k] = ((Vec0[k] * Fac2[k] - Vec1[k] * Fac4[k]) + Vec2[k] * Fac5[k]) * SignB[k];
+    }
+    const double Dot1 = (m[0][0] * inv[0][0] + m[0][1] * inv[1][0]) + (m[0][2] * inv[2][0] + m[0][3] * inv[3][0]);
+    const double OneOverDeterminant = 1.0 / Dot1;
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) out[4 * c + r] = (float)(inv[c][r] * OneOverDeterminant);
 }
 
 /* get_shift (internal_render.cpp:989-1016) + the border arithmetic of blockify_mesh (:1031-1041)

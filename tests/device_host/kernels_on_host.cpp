@@ -17,7 +17,8 @@ static void launch_pool(const SceneView &s, const UpdateArgs &a, long long nwg) 
 }
 template <int R>
 static void launch_wg(const SceneView &s, const UpdateArgs &a, long long nwg) {
-    emu_launch((unsigned)nwg, 1, R, [&] { radiance_update_wg_kernel<R, true>(s, a); });
+    // fewer CTAs than workgroups, as lumcu.cu caps the grid of this kernel: every CTA strides over ~3 workgroups
+    emu_launch((unsigned)((nwg + 2) / 3), 1, R, [&] { radiance_update_wg_kernel<R, true>(s, a); });
 }
 
 // Trace workgroups [0, nreq/size) of shard il into staged[] (validate_world_kernel first, like ensure_validated()).
@@ -26,7 +27,8 @@ static long long trace_on_host(int wx, int wy, int wz, int capacity, int brick0_
                                const int16_t *world, const uint8_t *bricks, const float *materials, const uint32_t *field_old,
                                const int16_t *requests, long long nreq, int time_seed, int size, int shift,
                                const float *table, const float *sun3, int variant, Interleave il, uint32_t *staged,
-                               float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals) {
+                               float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals,
+                               const PeerWords *inbox = nullptr, long long slack = 0) {
     if (size < 1 || shift < 0 || shift >= size || il.n < 1 || il.rank < 0 || il.rank >= il.n || il.chunk < 1) return -1;
     std::vector<float4> mat4(256);
     for (int i = 0; i < 256; i++) mat4[i] = make_float4(materials[6 * i], materials[6 * i + 1], materials[6 * i + 2], materials[6 * i + 4]);
@@ -34,11 +36,16 @@ static long long trace_on_host(int wx, int wy, int wz, int capacity, int brick0_
     uint32_t flags = 0;
     emu_launch(2, 1, 64, [&] { validate_world_kernel(world, cells, capacity, &flags); });
     const SceneView s{world, bricks, materials, mat4.data(), field_old, wx, wy, wz, capacity, brick0_empty, &flags};
-    const long long nwg_all = nreq / size;
+    // slack > 0: the host only knows an upper bound of the request count (lumcu_build_requests without a sync); the
+    // launch is sized for the bound and the kernels cut the dispatch down to the device-side count
+    const unsigned long long count = (unsigned long long)nreq;
+    const long long nwg_all = (nreq + slack) / size;
     UpdateArgs a{};
     a.requests = reinterpret_cast<const short4 *>(requests);
     a.dir_table = table;
     a.staged = staged;
+    if (inbox) a.inbox = *inbox;
+    if (slack > 0) a.nreq_dev = &count;
     a.dbg_pre_blend = pre_blend; a.dbg_samples = ray_samples; a.dbg_hits = ray_hits; a.dbg_totals = totals;
     a.wg_begin = 0; a.wg_end = nwg_all;
     a.il_chunk = il.chunk; a.il_rank = il.rank; a.il_n = il.n;
@@ -84,55 +91,73 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
                                       const uint32_t *field_old, uint32_t *field_new,
                                       const int16_t *requests, long long nreq, int time_seed, int size, int shift,
                                       const float *table, const float *sun3, int variant, int il_rank, int il_n,
-                                      float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals) {
-    const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? nreq / size : 0;
+                                      float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals,
+                                      long long slack) {
+    const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? (nreq + slack) / size : 0;
+    const unsigned long long count = (unsigned long long)nreq;
     std::vector<uint32_t> staged((size_t)std::max<long long>(nwg_all, 1));
     const Interleave il{IL_CHUNK, il_rank, il_n};
     const long long nwg = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials, field_old,
                                         requests, nreq, time_seed, size, shift, table, sun3, variant, il, staged.data(),
-                                        pre_blend, ray_samples, ray_hits, totals);
+                                        pre_blend, ray_samples, ray_hits, totals, nullptr, slack);
     if (nwg < 0) return -1;
     for (long long i = 0; i < cells; i++) field_new[i] = field_old[i];
     if (nwg == 0) return 0;
     const int ct = 64;
     emu_launch((unsigned)((nwg + ct - 1) / ct), 1, ct, [&] {
-        commit_kernel(field_new, staged.data(), reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, il);
+        commit_kernel(field_new, staged.data(), reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, il,
+                      slack > 0 ? &count : nullptr, ExchangeWait{});
     });
     return 0;
 }
 
-// One frame on `nranks` devices as lumcu_update_shard_exchange runs it: every rank traces its interleaved shard reading
-// its own replica of the field (all equal), then -- after what is peer_barrier_kernel(0) on the device -- stores its
-// texels into EVERY replica with commit_peers_kernel.  replicas: uint32 [nranks][cells], in = old field, out = new field.
-// il_chunk must be a multiple of the pooled kernel's probes per CTA (lumcu.cu uses 3072; small here so that a small
-// dispatch is really dealt to several ranks).
+// `frames` frames on `nranks` devices as lumcu_update_shard_exchange runs them: in epoch e every rank traces its
+// interleaved shard reading its own replica of the field, the new texels going into half e & 1 of EVERY rank's inbox
+// straight from the trace kernel; then arrive_kernel publishes e in every rank's flag array, and each rank's
+// commit_kernel -- which waits for all flags -- scatters the whole dispatch from its own inbox into its own replica.
+// (Ranks run one after another here, so every flag is already there when a commit looks; what is checked is the index
+// arithmetic, the parity halves and that every replica ends up equal to the single-device field.)
+// replicas: uint32 [nranks][cells], in = old field, out = field after the last frame.  il_chunk must be a multiple of
+// the pooled kernel's probes per CTA (lumcu.cu uses 3072; small here so that a small dispatch is really dealt out).
 extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
                                               const int16_t *world, const uint8_t *bricks, const float *materials,
                                               uint32_t *replicas, int nranks, int il_chunk,
                                               const int16_t *requests, long long nreq, int time_seed, int size, int shift,
-                                              const float *table, const float *sun3, int variant) {
+                                              const float *table, const float *sun3, int variant, int frames) {
     if (nranks < 1 || nranks > MAX_PEERS) return -1;
     const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? nreq / size : 0;
-    std::vector<std::vector<uint32_t>> staged((size_t)nranks, std::vector<uint32_t>((size_t)std::max<long long>(nwg_all, 1)));
-    std::vector<long long> traced((size_t)nranks);
+    const size_t half = (size_t)std::max<long long>(nwg_all, 1);
+    std::vector<std::vector<uint32_t>> staged((size_t)nranks, std::vector<uint32_t>(2 * half, 0xDEADBEEFu));
+    std::vector<std::vector<unsigned>> flags((size_t)nranks, std::vector<unsigned>(MAX_PEERS, 0u));
+    unsigned status = 0;
     unsigned long long tot[2];
-    for (int r = 0; r < nranks; r++) {
-        traced[r] = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials,
-                                  replicas + (size_t)r * cells, requests, nreq, time_seed, size, shift, table, sun3, variant,
-                                  Interleave{il_chunk, r, nranks}, staged[r].data(), nullptr, nullptr, nullptr, tot);
-        if (traced[r] < 0) return -1;
+    for (int f = 0; f < frames; f++) {
+        const unsigned epoch = (unsigned)f + 1u;
+        const int parity = (int)(epoch & 1u);
+        PeerWords inbox{};
+        inbox.n = nranks;
+        for (int p = 0; p < nranks; p++) inbox.p[p] = staged[p].data() + parity * half;
+        for (int r = 0; r < nranks; r++) {
+            const long long traced = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials,
+                                                   replicas + (size_t)r * cells, requests, nreq, time_seed + f, size, shift, table, sun3,
+                                                   variant, Interleave{il_chunk, r, nranks}, staged[r].data() + parity * half,
+                                                   nullptr, nullptr, nullptr, tot, &inbox);
+            if (traced < 0) return -1;
+            PeerFlags pf{};
+            pf.n = nranks; pf.rank = r;
+            for (int p = 0; p < nranks; p++) pf.f[p] = flags[p].data();
+            emu_launch(1, 1, 32, [&] { arrive_kernel(pf, epoch); });
+        }
+        const int ct = 64;
+        for (int r = 0; r < nranks; r++)
+            if (nwg_all > 0)
+                emu_launch((unsigned)((nwg_all + ct - 1) / ct), 1, ct, [&] {
+                    commit_kernel(replicas + (size_t)r * cells, staged[r].data() + parity * half, reinterpret_cast<const short4 *>(requests),
+                                  0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, Interleave{il_chunk, 0, 1}, nullptr,
+                                  ExchangeWait{flags[r].data(), nranks, epoch, 1ll << 40, &status});
+                });
     }
-    PeerFields pf{};
-    pf.n = nranks;
-    for (int p = 0; p < nranks; p++) pf.f[p] = replicas + (size_t)p * cells;
-    const int ct = 64;
-    for (int r = 0; r < nranks; r++)
-        if (traced[r] > 0)
-            emu_launch((unsigned)((traced[r] + ct - 1) / ct), 1, ct, [&] {
-                commit_peers_kernel(pf, staged[r].data(), reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift,
-                                    wx, wy, wz, -32768, 32768, Interleave{il_chunk, r, nranks});
-            });
-    return 0;
+    return status ? -2 : 0;
 }
 
 // The request-list builder as lumcu_build_requests launches it: count -> scan -> ordered scatter (-> specials).
@@ -146,17 +171,17 @@ extern "C" long long kernels_on_host_build_requests(int wx, int wy, int wz, cons
     std::vector<uint8_t> flags((size_t)cells);
     std::vector<uint32_t> counts((size_t)nblocks);
     std::vector<unsigned long long> offsets((size_t)nblocks);
-    unsigned long long total = 0;
+    unsigned long long total[2] = {0, 0};      // [0] the list, [1] its rule-built prefix
     short4 *o = reinterpret_cast<short4 *>(out);
     emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_count_kernel(world, wx, wy, wz, flags.data(), counts.data()); });
-    emu_launch(1, 1, 256, [&] { build_scan_kernel(counts.data(), offsets.data(), nblocks, &total); });
+    emu_launch(1, 1, 256, [&] { build_scan_kernel(counts.data(), offsets.data(), nblocks, total); });
     emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_scatter_kernel(flags.data(), offsets.data(), wx, wy, wz, o, cap); });
-    *nbuilt = (long long)total;
     if (nspecial > 0)
         emu_launch(1, 1, 256, [&] {
-            build_specials_kernel(flags.data(), wx, wy, wz, reinterpret_cast<const short4 *>(special), nspecial, o, &total, cap);
+            build_specials_kernel(flags.data(), wx, wy, wz, reinterpret_cast<const short4 *>(special), nspecial, o, total, cap);
         });
-    return (long long)total;
+    *nbuilt = (long long)total[1];
+    return (long long)total[0];
 }
 
 // shift_radiance as lumcu_shift launches it (tmp = copy of the field).

@@ -36,7 +36,7 @@ int main(int argc, char **argv) {
         unsigned long long tot[2];
         for (int variant : {1, 0}) {
             rc |= kernels_on_host_update(wx, wy, wz, P, 1, R, 0.01f, world.data(), bricks.data(), mats.data(), f0.data(), f1.data(),
-                                         req.data(), nreq, 3, 1, 0, table.data(), sun, variant, 0, 1, pre.data(), rs.data(), rh.data(), tot);
+                                         req.data(), nreq, 3, 1, 0, table.data(), sun, variant, 0, 1, pre.data(), rs.data(), rh.data(), tot, 0);
             std::printf("R=%d variant=%d: S=%llu H=%llu\n", R, variant, tot[0], tot[1]);
         }
     }

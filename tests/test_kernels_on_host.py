@@ -47,7 +47,7 @@ def emu():
     return build(OUT)
 
 
-def run(lib, O, scn, f0, req, seed, variant, rays=64, size=1, shift=0, reactiveness=0.01):
+def run(lib, O, scn, f0, req, seed, variant, rays=64, size=1, shift=0, reactiveness=0.01, slack=0):
     world = np.ascontiguousarray(scn["world"], np.int16)
     bricks = np.ascontiguousarray(scn["bricks"], np.uint8)
     mats = np.ascontiguousarray(scn["materials"], np.float32)
@@ -67,16 +67,16 @@ def run(lib, O, scn, f0, req, seed, variant, rays=64, size=1, shift=0, reactiven
                                     C.c_int(int(not bricks[0].any())), C.c_int(rays), C.c_float(reactiveness),
                                     p(world), p(bricks), p(mats), p(f0), p(f1), p(req), C.c_longlong(len(req)),
                                     C.c_int(seed), C.c_int(size), C.c_int(shift), p(table), p(sun), C.c_int(variant),
-                                    C.c_int(0), C.c_int(1), p(pre), p(rs), p(rh), p(tot))
+                                    C.c_int(0), C.c_int(1), p(pre), p(rs), p(rh), p(tot), C.c_longlong(slack))
     assert rc == 0
     return dict(field=f1, pre_blend=pre, ray_samples=rs, ray_hits=rh, totals=(int(tot[0]), int(tot[1])))
 
 
-def check(lib, O, scn, req, seed, variant, rays=64, size=1, shift=0, field_seed=3):
+def check(lib, O, scn, req, seed, variant, rays=64, size=1, shift=0, field_seed=3, slack=0):
     sc = scene_of(O, scn, rays=rays)
     f0 = np.random.default_rng(field_seed).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
     ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=True)
-    got = run(lib, O, scn, f0, req, seed, variant, rays=rays, size=size, shift=shift)
+    got = run(lib, O, scn, f0, req, seed, variant, rays=rays, size=size, shift=shift, slack=slack)
     assert_same(got, ref)
     assert got["totals"] == ref["totals"][:2]
 
@@ -86,6 +86,16 @@ def test_demo_world_kernels(emu, oracle_mod, demo, variant):
     """61 probes of the demo world (a ragged last batch for the pooled kernel: 10 full CTAs + 1 probe)."""
     O = oracle_mod
     check(emu, O, demo, O.build_requests(demo["world"])[1000:1061], 5, variant)
+
+
+@pytest.mark.parametrize("variant", [POOL, WG], ids=["pooled", "workgroup"])
+def test_dispatch_cut_down_to_device_side_count(emu, oracle_mod, demo, variant):
+    """lumcu_build_requests without a host sync: the launch is sized for an upper bound (here 100 requests more than the
+    list holds) and trace and commit kernels stop at the count they read from device memory."""
+    O = oracle_mod
+    req = O.build_requests(demo["world"])[1000:1061]
+    check(emu, O, demo, req, 5, variant, slack=100)
+    check(emu, O, demo, req[:60], 6, variant, size=3, shift=1, slack=7)
 
 
 @pytest.mark.parametrize("rays", [16, 64, 256])
@@ -223,13 +233,16 @@ def test_slab_bound_kernel(emu, oracle_mod, demo):
 
 @pytest.mark.parametrize("nranks,variant", [(2, POOL), (3, POOL), (2, WG)])
 def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant):
-    """SURVEY 8e on the emulator: the dispatch dealt to `nranks` ranks in interleaved chunks (il_map in the kernels), every
-    rank's texels stored into every replica by commit_peers_kernel -- all replicas equal the single-device field."""
+    """SURVEY 8e on the emulator: three frames dealt to `nranks` ranks in interleaved chunks (il_map in the kernels), every
+    rank's texels stored into every rank's inbox from the trace kernel (alternating halves), arrive_kernel, then each rank's
+    commit_kernel behind the flag wait -- all replicas equal the single-device field after every frame."""
     O = oracle_mod
     sc = scene_of(O, small_synth)
     req = np.ascontiguousarray(O.build_requests(small_synth["world"])[::53][:45], np.int16)      # 45 probes, chunks of 12
     f0 = np.random.default_rng(8).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
-    ref = O.update(sc, f0, req, 4)["field"]
+    ref = f0
+    for f in range(3):
+        ref = O.update(sc, ref, req, 4 + f)["field"]
     world = np.ascontiguousarray(small_synth["world"], np.int16)
     bricks = np.ascontiguousarray(small_synth["bricks"], np.uint8)
     mats = np.ascontiguousarray(small_synth["materials"], np.float32)
@@ -242,7 +255,7 @@ def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nrank
     rc = emu.kernels_on_host_update_sharded(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]), C.c_int(1),
                                             C.c_int(64), C.c_float(0.01), p(world), p(bricks), p(mats), p(replicas),
                                             C.c_int(nranks), C.c_int(12), p(req), C.c_longlong(len(req)), C.c_int(4),
-                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant))
+                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant), C.c_int(3))
     assert rc == 0
     for r in range(nranks):
         assert np.array_equal(replicas[r], ref), r

@@ -37,7 +37,7 @@ for f in range(4):
         D.all_gather_field(field, (wx, wy, wz), rank, world)
 out = st.download_field()
 np.save(os.path.join(os.environ["OUT_DIR"], f"f{rank}.npy"), out)
-# the same four frames with the exchange fused into the commit (peer stores + flag barriers)
+# the same four frames with the exchange fused into the trace (peer stores into every rank's inbox, one flag barrier)
 st.upload_field(np.zeros(st.cells, np.uint32)); st.wait_idle(); dist.barrier()
 D.open_peer_exchange(st, rank, world, device=f"cuda:{rank}")
 for f in range(4):
@@ -52,6 +52,30 @@ for f in range(4):
 out = st.download_field()
 dist.barrier()
 np.save(os.path.join(os.environ["OUT_DIR"], f"h{rank}.npy"), out)
+st.peers_close()
+dist.barrier()
+st.close()
+# a dispatch of many chunks per rank (pooled kernel, peer stores and commits of neighbouring frames in flight together),
+# random initial field, the request list rebuilt before every frame WITHOUT a host sync (the count stays on the device)
+sc = scenes.synthetic_scene(96, 80, 32, palette=64, seed=9)
+wz, wy, wx = sc["world"].shape
+st = lum_b200.RadianceStage((wx, wy, wz), 64, device=rank)
+st.upload_world(sc["world"]); st.upload_bricks(0, sc["bricks"]); st.upload_materials(sc["materials"])
+f0 = np.random.default_rng(31).integers(0, 2 ** 32, st.cells, dtype=np.uint64).astype(np.uint32)
+st.upload_field(f0); st.wait_idle()
+D.open_peer_exchange(st, rank, world, device=f"cuda:{rank}")
+for f in range(5):
+    st.build_requests(sp, sync=False)
+    st.update_shard_exchange(100 + f, 1, 0)
+out = st.download_field()
+dist.barrier()
+np.save(os.path.join(os.environ["OUT_DIR"], f"k{rank}.npy"), out)
+# magicSize dispatches (size 3, shift = frame % 3) through the same exchange
+for f in range(3):
+    st.update_shard_exchange(200 + f, 3, f % 3)
+out = st.download_field()
+dist.barrier()
+np.save(os.path.join(os.environ["OUT_DIR"], f"m{rank}.npy"), out)
 st.peers_close()
 dist.barrier(); dist.destroy_process_group()
 '''
@@ -84,6 +108,25 @@ def test_two_gpu_slabs_match_single_gpu(tmp_path):
     assert np.array_equal(ga, ref) and np.array_equal(gb, ref)        # fused exchange: same bits
     ha, hb = np.load(tmp_path / "h0.npy"), np.load(tmp_path / "h1.npy")
     assert np.array_equal(ha, ref) and np.array_equal(hb, ref)        # interleaved shards: same bits
+    st.close()
+    # the large dispatch: five frames from a random field, list rebuilt without a sync before each
+    sc = scenes.synthetic_scene(96, 80, 32, palette=64, seed=9)
+    st = lum_b200.RadianceStage((96, 80, 32), 64)
+    st.upload_world(sc["world"]); st.upload_bricks(0, sc["bricks"]); st.upload_materials(sc["materials"])
+    n = st.build_requests(np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16))
+    assert n > 20 * 3072
+    st.upload_field(np.random.default_rng(31).integers(0, 2 ** 32, st.cells, dtype=np.uint64).astype(np.uint32))
+    for f in range(5):
+        st.update(100 + f)
+    ref = st.download_field()
+    ka, kb = np.load(tmp_path / "k0.npy"), np.load(tmp_path / "k1.npy")
+    assert np.array_equal(ka, kb)
+    assert np.array_equal(ka, ref)
+    for f in range(3):
+        st.update(200 + f, 3, f % 3)
+    ref = st.download_field()
+    ma, mb = np.load(tmp_path / "m0.npy"), np.load(tmp_path / "m1.npy")
+    assert np.array_equal(ma, ref) and np.array_equal(mb, ref)
 
 
 def test_peer_exchange_single_rank_degenerates_to_update(oracle_mod, demo):

@@ -458,3 +458,89 @@ def test_random_small_worlds(oracle_mod, case):
     size = min(size, len(req))
     assert_update_equal(st, O, sc, f0, req, int(rng.integers(-2 ** 31, 2 ** 31)), size=size, shift=int(rng.integers(0, size)))
     st.close()
+
+
+def test_slab_update_is_jacobi_across_its_two_passes(oracle_mod, demo):
+    """lumcu_update_slab traces the slab's sorted range and then the unsorted special tail: the tail's rays must see
+    the field as it was BEFORE the frame even where they land on texels of the sorted range (the first
+    pass used to commit before the second one traced).  Specials sit in air right above the ground probes of their own
+    slab, the field is random, one slab covers the whole world -- so the tail's gathers hit texels the first pass
+    rewrites."""
+    O = oracle_mod
+    sc = oracle_scene(O, demo)
+    rule = O.build_requests(demo["world"])
+    sel = np.zeros((16, 48, 48), bool)
+    sel[rule[:, 2], rule[:, 1], rule[:, 0]] = True
+    # unselected cells directly above a selected one: their probe rays start next to updated texels
+    cand = np.argwhere(~sel[1:] & sel[:-1])[:40]
+    sp = np.array([(x, y, z + 1, 0) for z, y, x in cand], np.int16)[::-1].copy()      # descending: an unsorted tail
+    assert len(sp) >= 20
+    req = O.build_requests(demo["world"], sp)
+    assert len(req) == len(rule) + len(sp)
+    f0 = np.random.default_rng(77).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = O.update(sc, f0, req, 3)["field"]
+    st = make_stage(demo)
+    st.build_requests(sp)
+    assert np.array_equal(st.download_requests(), req)
+    st.upload_field(f0)
+    st.update_slab(3, 1, 0, 0, 16)
+    assert np.array_equal(st.download_field(), ref)
+    # unbounded slab arguments mean the whole list (the predecessor of the first workgroup is z = -32768)
+    assert st.slab_range(1, 0, -40000, 40000) == (0, len(rule))
+    st.upload_field(f0)
+    st.update_slab(3, 1, 0, -2 ** 31, 2 ** 31 - 1)
+    assert np.array_equal(st.download_field(), ref)
+    st.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_async_build_and_device_side_count(oracle_mod, demo, variant):
+    """lumcu_build_requests(out_count = NULL): nothing waits for the GPU, the launches are sized for an upper bound of
+    the request count (14x the real one on the demo world) and the kernels stop at the count they read on the device.
+    Two frames queued back to back, world uploaded from pinned memory without a wait, result read back through the
+    asynchronous download + fence: equal to the synchronous path and to the oracle."""
+    import torch
+    O = oracle_mod
+    sc = oracle_scene(O, demo)
+    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0)], np.int16)
+    req = O.build_requests(demo["world"], sp)
+    f0 = np.random.default_rng(5).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+    ref = f0
+    for f in range(2):
+        ref = O.update(sc, ref, req, 40 + f)["field"]
+    st = make_stage(demo)
+    st.set_kernel_variant(variant)
+    pin_w = torch.empty(sc.cells, dtype=torch.int16, pin_memory=True)
+    pin_f = torch.empty(sc.cells, dtype=torch.int32, pin_memory=True)
+    pin_w.numpy()[:] = np.ascontiguousarray(demo["world"], np.int16).reshape(-1)
+    st.upload_field(f0)
+    for f in range(2):
+        st.upload_world_async(pin_w.numpy())
+        assert st.build_requests(sp, sync=False) is None
+        st.update(40 + f)
+    out = pin_f.numpy().view(np.uint32)
+    st.download_field_async(out)
+    st.record_fence(1)
+    st.wait_fence(1)
+    assert np.array_equal(out, ref)
+    assert st.request_count() == len(req)                      # the host learns the count when it asks
+    assert np.array_equal(st.download_requests(), req)
+    st.wait_fence(3)                                           # never recorded: returns at once
+    st.close()
+    del pin_w, pin_f
+
+
+def test_brick_copy_list_must_not_alias(demo):
+    import lum_b200
+    st = make_stage(demo, max_requests=0)
+    with pytest.raises(lum_b200.LumcuError):
+        st.copy_bricks([1, 2], [9, 9])                         # one destination twice
+    st.close()
+    st = lum_b200.RadianceStage((48, 48, 16), 32)
+    st.upload_world(demo["world"]); st.upload_bricks(0, demo["bricks"]); st.upload_materials(demo["materials"])
+    with pytest.raises(lum_b200.LumcuError):
+        st.copy_bricks([1, 20], [20, 21])                      # a destination that is also a source
+    st.copy_bricks([1, 2], [20, 21])
+    got = st.download_bricks(20, 2)
+    assert np.array_equal(got, demo["bricks"][1:3])
+    st.close()

@@ -149,3 +149,37 @@ def test_malformed_files_are_rejected(tmp_path):
         clum.read_vox(p)
     with pytest.raises(ValueError):
         clum.read_vox(str(tmp_path / "missing.vox"))
+
+
+def _raw_vox(chunks):
+    body = b"".join(cid + struct.pack("<II", len(c), 0) + c for cid, c in chunks)
+    return b"VOX " + struct.pack("<I", 150) + b"MAIN" + struct.pack("<II", 0, len(body)) + body
+
+
+def test_hostile_size_chunk_is_rejected(tmp_path):
+    """three unchecked 32-bit sizes whose product wraps to a small allocation (2^22 * 2^21 * 2^21 = 0
+    mod 2^64) let a crafted file write out of bounds; XYZI coordinates are bytes, so no valid file exceeds 256."""
+    p = str(tmp_path / "wrap.vox")
+    open(p, "wb").write(_raw_vox([(b"SIZE", struct.pack("<III", 1 << 22, 1 << 21, 1 << 21)),
+                                  (b"XYZI", struct.pack("<I", 1) + bytes([200, 200, 200, 7]))]))
+    with pytest.raises(ValueError):
+        clum.read_vox(p)
+    open(p, "wb").write(_raw_vox([(b"SIZE", struct.pack("<III", 257, 4, 4)),
+                                  (b"XYZI", struct.pack("<I", 1) + bytes([1, 1, 1, 7]))]))
+    with pytest.raises(ValueError):
+        clum.read_vox(p)
+    open(p, "wb").write(_raw_vox([(b"SIZE", struct.pack("<III", 256, 2, 2)),          # the limit itself is fine
+                                  (b"XYZI", struct.pack("<I", 1) + bytes([255, 1, 1, 7]))]))
+    assert clum.read_vox(p)[0].shape == (2, 2, 256)
+
+
+def test_imap_that_is_not_a_permutation(tmp_path):
+    """Stored indices no IMAP entry names map to display index 0 (+1), not to whatever the stack held."""
+    p = str(tmp_path / "imap.vox")
+    v = np.zeros((2, 2, 2), np.uint8); v[0, 0, 0] = 9; v[1, 1, 1] = 200
+    imap = np.full(256, 9, np.uint8)                      # every display index -> stored 9; 200 is never named
+    write_vox(p, v, imap=imap)
+    a, b = clum.read_vox(p)[0], clum.read_vox(p)[0]
+    assert np.array_equal(a, b)                           # deterministic
+    assert a[1, 1, 1] == 1                                # 1 + inv[200], inv zero-initialised
+    assert a[0, 0, 0] == 0                                # 1 + inv[9] = 1 + 255 (the last display index naming 9), as a byte
