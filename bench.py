@@ -634,7 +634,7 @@ def run_ours(args, rank, local_rank, world_size):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": rays,
-                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + ("interleaved chunks of 3072; the trace kernel stores each new texel into every rank's inbox over NVLink, one flag barrier, local commit"
+                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + ("contiguous equal ranges of the dispatch; the trace kernel stores each new texel into every rank's inbox over NVLink, one flag barrier, local commit"
                                                                              if runner.fused else "z-slabs + NCCL field all-gather"))
                            if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
                            "time_seed": "step index", "initial_field": "zero"},

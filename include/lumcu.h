@@ -140,12 +140,19 @@ int lumcu_peers_open(LumcuCtx *ctx, int32_t rank, int32_t nranks, const uint8_t 
 int lumcu_peers_close(LumcuCtx *ctx);
 int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift,
                                int32_t z_begin, int32_t z_end);
-/* Interleaved probe sharding: the dispatch's workgroups are cut into chunks of 3072 and shard `rank` of `nranks`
- * takes chunks rank, rank + nranks, ...  Unlike z-slabs this balances the ranks whatever the scene looks like
- * (every rank samples every part of the world); it needs the texel-wise exchange, since a shard's texels are
- * not contiguous in the field.  lumcu_update_shard: trace + local commit of one shard (the union over all
- * shards, each from the same starting field, equals lumcu_update).  lumcu_update_shard_exchange: the per-frame
- * call of step 4 above with this sharding (rank and nranks as given to lumcu_peers_open). */
+/* Probe sharding by workgroup index (no z-sorted list needed).  lumcu_set_shard_mode chooses how the dispatch's
+ * workgroups are dealt to `nranks` shards:
+ *   LUMCU_SHARD_CONTIGUOUS (default)  shard r takes workgroups [T*r/n, T*(r+1)/n) of the dispatch's T: equal probe
+ *       counts whatever the scene looks like, and each rank touches only its own part of world and field;
+ *   LUMCU_SHARD_INTERLEAVED           the dispatch is cut into chunks of 3072 workgroups and shard r takes chunks
+ *       r, r + n, ...: every rank samples every part of the world, which also balances the COST per probe when that
+ *       varies by region, at the price of every rank pulling the whole scene through its caches.
+ * Both need the texel-wise exchange (a shard's texels are not a slab of the field).  lumcu_update_shard: trace + local
+ * commit of one shard (the union over all shards, each from the same starting field, equals lumcu_update).
+ * lumcu_update_shard_exchange: the per-frame call of step 4 above (rank and nranks as given to lumcu_peers_open). */
+#define LUMCU_SHARD_CONTIGUOUS 0
+#define LUMCU_SHARD_INTERLEAVED 1
+int lumcu_set_shard_mode(LumcuCtx *ctx, int32_t mode);
 int lumcu_update_shard(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift, int32_t rank, int32_t nranks);
 int lumcu_update_shard_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift);
 

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("LUMCU_LIB") or os.path.join(HERE, "liblumcu.so")   # 
 
 DEBUG_PRE_BLEND = 1
 DEBUG_RAYS = 2
+SHARD_CONTIGUOUS, SHARD_INTERLEAVED = 0, 1      # lumcu_set_shard_mode
 
 _lib = None
 
@@ -83,6 +84,7 @@ SYMBOLS = {
     "lumcu_last_update_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lumcu_set_kernel_variant": (C.c_int, [_P, C.c_int32]),
     "lumcu_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "lumcu_set_shard_mode": (C.c_int, [_P, C.c_int32]),
     "lumcu_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lumcu_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "lumcu_glossy": (C.c_int, [_P, C.POINTER(LumcuGlossyView), C.c_int32, C.c_int32, _P, _P, _P, _P]),
@@ -349,6 +351,10 @@ class RadianceStage:
 
     def set_kernel_variant(self, variant):
         self._ck(self.lib.lumcu_set_kernel_variant(self.ctx, int(variant)))
+
+    def set_shard_mode(self, mode):
+        """SHARD_CONTIGUOUS (default) or SHARD_INTERLEAVED (lumcu_set_shard_mode)."""
+        self._ck(self.lib.lumcu_set_shard_mode(self.ctx, int(mode)))
 
     def set_profiling(self, on):
         self._ck(self.lib.lumcu_set_profiling(self.ctx, int(bool(on))))

@@ -80,12 +80,19 @@ struct LumcuCtx {
     long long max_requests = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;    // uploads from caller-pinned memory (no staging copy)
+    cudaStream_t dl_stream = nullptr;      // lumcu_download_field_async: D2H beside the next frame's trace and upload
+    cudaEvent_t ev_dl_ready = nullptr, ev_dl_done = nullptr;
+    bool dl_pending = false;               // a D2H of the field is in flight on dl_stream: the next writer of the field waits for it
     cudaEvent_t ev_compute = nullptr, ev_copy = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-    cudaEvent_t fences[LUMCU_FENCES] = {};  // lumcu_record_fence / lumcu_wait_fence (created on first use)
+    cudaEvent_t fences[2 * LUMCU_FENCES] = {};  // lumcu_record_fence / lumcu_wait_fence: [2*slot] stream, [2*slot+1] dl_stream
     bool timed = false, profiling = false, ktimed = false;
 
-    int16_t *d_world = nullptr;
+    int16_t *d_world = nullptr;            // = d_world_buf[world_cur]: the world the next launches read
+    int16_t *d_world_buf[2] = {nullptr, nullptr};   // two buffers: lumcu_upload_world_async fills the other one while
+    int world_cur = 0;                              // the frame in flight still reads this one, then flips
+    cudaEvent_t ev_world_retired[2] = {nullptr, nullptr};   // "everything queued before the flip away from buffer b has run"
+    bool world_retired[2] = {false, false};
     uint8_t *d_bricks = nullptr;
     float *d_materials = nullptr;
     float4 *d_mat4 = nullptr;              // {r,g,b,emmit} per id, repacked at upload (the shading phase's one load)
@@ -105,6 +112,7 @@ struct LumcuCtx {
     int sm_count = 148;          // cudaDevAttrMultiProcessorCount (grid sizing of the grid-stride kernels)
     int pool_threads = 128;      // tuning knobs (env LUMCU_POOL_THREADS / LUMCU_CARVEOUT, read at create)
     int carveout = -1;
+    int shard_chunk = 0;         // lumcu_set_shard_mode: 0 = contiguous shards (default), IL_CHUNK = interleaved chunks
     int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
     bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
     uint32_t *d_scene_flags = nullptr;     // bit 0: world ids outside the palette (validate_world_kernel)
@@ -113,8 +121,7 @@ struct LumcuCtx {
 
     // builder scratch (lazy)
     uint8_t *d_flags = nullptr;
-    uint32_t *d_block_counts = nullptr;
-    unsigned long long *d_block_offsets = nullptr;
+    unsigned long long *d_tile_state = nullptr;   // build_fused_kernel's look-back states + its ticket counter
     unsigned long long *d_total = nullptr;      // [0] = requests in the list, [1] = of which built by the 3x3x3 rule (z-sorted)
     short4 *d_special = nullptr;
     long long special_cap = 0;
@@ -278,6 +285,7 @@ SceneView scene_view(LumcuCtx *c) {
 // number of workgroups of [0, total) that shard `il` owns
 long long il_count(long long total, const Interleave &il) {
     if (il.n <= 1) return total;
+    if (il.chunk == 0) return (total + il.n - 1) / il.n;      // contiguous: the largest shard (also covers a device-side count below the bound)
     const long long full = total / il.chunk, rem = total % il.chunk;
     return (full / il.n) * il.chunk + ((full % il.n) > il.rank ? il.chunk : 0) + ((full % il.n) == il.rank ? rem : 0);
 }
@@ -301,6 +309,16 @@ int resolve_count(LumcuCtx *c) {
     return 0;
 }
 
+// A lumcu_download_field_async may still be reading the field on the download stream: whoever writes the field next
+// (a commit, a shift, an upload) is queued behind it.
+int before_field_write(LumcuCtx *c) {
+    if (c->dl_pending) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_dl_done, 0));
+        c->dl_pending = false;
+    }
+    return 0;
+}
+
 uint32_t *staged_half(LumcuCtx *c, int parity) { return c->d_staged + (size_t)parity * (size_t)c->max_requests; }
 
 // xw.flags != null: a multi-GPU frame -- the staged half is this rank's inbox and the kernel waits for every rank's arrival
@@ -308,6 +326,7 @@ int commit_local(LumcuCtx *c, int size, int shift, long long wg_begin, long long
                  Interleave il = Interleave{IL_CHUNK, 0, 1}, int parity = 0, ExchangeWait xw = ExchangeWait{}) {
     const long long nwg = il_count(wg_end - wg_begin, il);
     if (nwg <= 0) return 0;
+    if (int rc = before_field_write(c)) return rc;
     const int ct = 256;
     commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
         c->d_field, staged_half(c, parity), c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il,
@@ -421,19 +440,26 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     c->R = R;
     c->cells = (long long)c->wx * c->wy * c->wz;
     c->max_requests = d->max_requests > 0 ? d->max_requests : c->cells + 4096;
+    if (c->max_requests >= (1ll << 32)) { delete c; return fail(LUMCU_E_ARG, "max_requests must fit 32 bits"); }
     auto bail = [&](int rc) { lumcu_destroy(c); return rc; };
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(LUMCU_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); } while (0)
     CUB(cudaSetDevice(d->device));
     CUB(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, d->device));
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUB(cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_dl_ready, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_dl_done, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_world_retired[0], cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_world_retired[1], cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     CUB(cudaEventCreate(&c->ev_begin));
     CUB(cudaEventCreate(&c->ev_end));
     CUB(cudaEventCreate(&c->ev_k0));
     CUB(cudaEventCreate(&c->ev_k1));
-    CUB(cudaMalloc(&c->d_world, (size_t)c->cells * sizeof(int16_t)));
+    CUB(cudaMalloc(&c->d_world_buf[0], (size_t)c->cells * sizeof(int16_t)));
+    c->d_world = c->d_world_buf[0];        // (the second buffer is allocated by the first lumcu_upload_world_async)
     CUB(cudaMalloc(&c->d_scene_flags, sizeof(uint32_t)));
     CUB(cudaMalloc(&c->d_bricks, (size_t)d->palette_capacity * 4096));
     CUB(cudaMalloc(&c->d_materials, 256 * 6 * sizeof(float)));
@@ -450,6 +476,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     if (const char *e = getenv("LUMCU_POOL_THREADS")) c->pool_threads = atoi(e) == 256 ? 256 : 128;
     if (const char *e = getenv("LUMCU_CARVEOUT")) c->carveout = atoi(e);
     if (const char *e = getenv("LUMCU_KERNEL_VARIANT")) c->kernel_variant = atoi(e);
+    if (const char *e = getenv("LUMCU_SHARD_MODE")) c->shard_chunk = atoi(e) == LUMCU_SHARD_INTERLEAVED ? IL_CHUNK : 0;
     host_direction_table(R, c->h_table);
     CUB(cudaMemcpyAsync(c->d_table, c->h_table.data(), (size_t)R * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     {   // normalize(vec3(0.5,0.5,-0.9)) (radiance.comp:42), f32, x->y->z dot
@@ -467,11 +494,13 @@ int lumcu_destroy(LumcuCtx *c) {
     if (!c) return 0;
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->dl_stream) cudaStreamSynchronize(c->dl_stream);
     cudaFree(c->d_scene_flags);
     cudaFree(c->d_g_matnorm); cudaFree(c->d_g_depth); cudaFree(c->d_g_frame); cudaFree(c->d_g_cov);
-    cudaFree(c->d_world); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_mat4); cudaFree(c->d_field);
+    cudaFree(c->d_world_buf[0]); cudaFree(c->d_world_buf[1]); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_mat4); cudaFree(c->d_field);
     cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
-    cudaFree(c->d_flags); cudaFree(c->d_block_counts); cudaFree(c->d_block_offsets); cudaFree(c->d_total);
+    cudaFree(c->d_flags); cudaFree(c->d_tile_state); cudaFree(c->d_total);
     lumcu_peers_close(c);
     cudaFree(c->d_sync_flags);
     if (c->h_status) cudaFreeHost(c->h_status);
@@ -486,13 +515,17 @@ int lumcu_destroy(LumcuCtx *c) {
     if (c->ev_k1) cudaEventDestroy(c->ev_k1);
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->ev_dl_ready) cudaEventDestroy(c->ev_dl_ready);
+    if (c->ev_dl_done) cudaEventDestroy(c->ev_dl_done);
+    for (auto &e : c->ev_world_retired) if (e) cudaEventDestroy(e);
+    if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
 }
 
-static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, size_t bytes, bool wait = true) {
+static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, size_t bytes) {
     // Caller buffer already page-locked (cudaHostAlloc / cudaHostRegister): copy straight from it on
     // the copy stream -- ordered after the work already queued (the kernels still reading dst) and
     // before whatever is queued next -- and return once the copy itself is done, so the buffer is
@@ -504,7 +537,7 @@ static int staged_upload(LumcuCtx *c, Staging &st, void *dst, const void *src, s
         CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->ev_copy, c->copy_stream));
         CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
-        if (wait) CU(cudaEventSynchronize(c->ev_copy));      // (!wait: the caller keeps the buffer untouched, lumcu_upload_world_async)
+        CU(cudaEventSynchronize(c->ev_copy));
         return 0;
     }
     cudaGetLastError();   // cudaPointerGetAttributes on plain pageable memory may leave an error state on old drivers
@@ -528,7 +561,25 @@ int lumcu_upload_world(LumcuCtx *c, const int16_t *world) {
 int lumcu_upload_world_async(LumcuCtx *c, const int16_t *world) {
     if (int rc = use(c)) return rc;
     if (!world) return fail(LUMCU_E_ARG, "null world");
-    if (int rc = staged_upload(c, c->stage_world, c->d_world, world, (size_t)c->cells * sizeof(int16_t), false)) return rc;
+    const size_t bytes = (size_t)c->cells * sizeof(int16_t);
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, world) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return lumcu_upload_world(c, world);                       // pageable memory: the synchronous path
+    }
+    // The frame in flight still reads the current buffer, so the copy goes into the OTHER one, on the copy stream,
+    // beside that frame's tracing.  It only has to wait for whoever last read the other buffer -- everything that was
+    // queued before the previous flip (ev_world_retired) -- and the launches queued from here on wait for the copy.
+    const int cur = c->world_cur, nxt = cur ^ 1;
+    if (!c->d_world_buf[nxt]) CU(cudaMalloc(&c->d_world_buf[nxt], bytes));
+    CU(cudaEventRecord(c->ev_world_retired[cur], c->stream));      // every reader of `cur` has been queued by now
+    c->world_retired[cur] = true;
+    if (c->world_retired[nxt]) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_world_retired[nxt], 0));
+    CU(cudaMemcpyAsync(c->d_world_buf[nxt], world, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    c->world_cur = nxt;
+    c->d_world = c->d_world_buf[nxt];
     c->have_world = true;
     c->world_dirty = true;
     return 0;
@@ -693,17 +744,17 @@ int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, 
     if (int rc = use(c)) return rc;
     if (!c->have_world) return fail(LUMCU_E_STATE, "lumcu_build_requests before lumcu_upload_world");
     if (nspecial < 0 || (nspecial > 0 && !special)) return fail(LUMCU_E_ARG, "bad special requests");
-    const long long nblocks = (c->cells + BUILD_THREADS - 1) / BUILD_THREADS;
+    const long long ntiles = (c->cells + BUILD_TILE - 1) / BUILD_TILE;
     if (!c->d_flags) {
         CU(cudaMalloc(&c->d_flags, (size_t)c->cells));
-        CU(cudaMalloc(&c->d_block_counts, (size_t)nblocks * sizeof(uint32_t)));
-        CU(cudaMalloc(&c->d_block_offsets, (size_t)nblocks * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->d_tile_state, ((size_t)ntiles + 1) * sizeof(unsigned long long)));     // [ntiles] = the ticket counter
         CU(cudaMalloc(&c->d_total, 2 * sizeof(unsigned long long)));
     }
-    build_count_kernel<<<(unsigned)nblocks, BUILD_THREADS, 0, c->stream>>>(c->d_world, c->wx, c->wy, c->wz, c->d_flags, c->d_block_counts);
-    build_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_block_counts, c->d_block_offsets, nblocks, c->d_total);
-    build_scatter_kernel<<<(unsigned)nblocks, BUILD_THREADS, 0, c->stream>>>(c->d_flags, c->d_block_offsets, c->wx, c->wy, c->wz, c->d_requests, c->max_requests);
-    c->launches += 3;
+    CU(cudaMemsetAsync(c->d_tile_state, 0, ((size_t)ntiles + 1) * sizeof(unsigned long long), c->stream));
+    build_fused_kernel<<<(unsigned)ntiles, BUILD_THREADS, 0, c->stream>>>(c->d_world, c->wx, c->wy, c->wz, c->d_flags, c->d_tile_state,
+                                                                        (unsigned int *)(c->d_tile_state + ntiles), c->d_requests,
+                                                                        c->max_requests, c->d_total);
+    c->launches++;
     CU(cudaGetLastError());
     if (nspecial > 0) {
         if (c->special_cap < nspecial) {
@@ -896,7 +947,7 @@ int lumcu_update_shard(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shi
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
     if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
     CU(cudaEventRecord(c->ev_begin, c->stream));
-    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, Interleave{IL_CHUNK, rank, nranks})) return rc;
+    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, Interleave{c->shard_chunk, rank, nranks})) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;
@@ -934,7 +985,7 @@ int lumcu_update_shard_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, in
     if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
     if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
-    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, Interleave{IL_CHUNK, c->peer_rank, c->peer_n});
+    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, Interleave{c->shard_chunk, c->peer_rank, c->peer_n});
 }
 
 int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
@@ -949,6 +1000,7 @@ int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int
 int lumcu_shift(LumcuCtx *c, int32_t dx, int32_t dy, int32_t dz) {
     if (int rc = use(c)) return rc;
     if ((dx == 0 && dy == 0 && dz == 0) || abs(dx) >= c->wx || abs(dy) >= c->wy || abs(dz) >= c->wz) return 0;
+    if (int rc = before_field_write(c)) return rc;
     if (!c->d_field_tmp) CU(cudaMalloc(&c->d_field_tmp, (size_t)c->cells * sizeof(uint32_t)));
     CU(cudaMemcpyAsync(c->d_field_tmp, c->d_field, (size_t)c->cells * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
     const int t = 256;
@@ -961,6 +1013,7 @@ int lumcu_shift(LumcuCtx *c, int32_t dx, int32_t dy, int32_t dz) {
 int lumcu_upload_field(LumcuCtx *c, const uint32_t *f) {
     if (int rc = use(c)) return rc;
     if (!f) return fail(LUMCU_E_ARG, "null field");
+    if (int rc = before_field_write(c)) return rc;
     return staged_upload(c, c->stage_misc, c->d_field, f, (size_t)c->cells * sizeof(uint32_t));
 }
 
@@ -975,22 +1028,32 @@ int lumcu_download_field(LumcuCtx *c, uint32_t *f) {
 int lumcu_download_field_async(LumcuCtx *c, uint32_t *out, int64_t first, int64_t count) {
     if (int rc = use(c)) return rc;
     if (!out || first < 0 || count < 0 || first + count > c->cells) return fail(LUMCU_E_ARG, "bad field range [%lld, +%lld)", (long long)first, (long long)count);
-    if (count > 0) CU(cudaMemcpyAsync(out, c->d_field + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (count == 0) return 0;
+    // on its own stream, behind what is queued so far (the commit that produced the field) and beside what comes next
+    // (the next frame's upload, build and trace, none of which write the field; its commit waits: before_field_write)
+    CU(cudaEventRecord(c->ev_dl_ready, c->stream));
+    CU(cudaStreamWaitEvent(c->dl_stream, c->ev_dl_ready, 0));
+    CU(cudaMemcpyAsync(out, c->d_field + first, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->dl_stream));
+    CU(cudaEventRecord(c->ev_dl_done, c->dl_stream));
+    c->dl_pending = true;
     return 0;
 }
 
 int lumcu_record_fence(LumcuCtx *c, int32_t slot) {
     if (int rc = use(c)) return rc;
     if (slot < 0 || slot >= LUMCU_FENCES) return fail(LUMCU_E_ARG, "fence slot %d outside [0,%d)", slot, LUMCU_FENCES);
-    if (!c->fences[slot]) CU(cudaEventCreateWithFlags(&c->fences[slot], cudaEventDisableTiming));
-    CU(cudaEventRecord(c->fences[slot], c->stream));
+    for (int k = 0; k < 2; k++)
+        if (!c->fences[2 * slot + k]) CU(cudaEventCreateWithFlags(&c->fences[2 * slot + k], cudaEventDisableTiming));
+    CU(cudaEventRecord(c->fences[2 * slot], c->stream));           // the stage's stream ...
+    CU(cudaEventRecord(c->fences[2 * slot + 1], c->dl_stream));    // ... and the downloads queued so far
     return 0;
 }
 
 int lumcu_wait_fence(LumcuCtx *c, int32_t slot) {
     if (int rc = use(c)) return rc;
     if (slot < 0 || slot >= LUMCU_FENCES) return fail(LUMCU_E_ARG, "fence slot %d outside [0,%d)", slot, LUMCU_FENCES);
-    if (c->fences[slot]) CU(cudaEventSynchronize(c->fences[slot]));
+    for (int k = 0; k < 2; k++)
+        if (c->fences[2 * slot + k]) CU(cudaEventSynchronize(c->fences[2 * slot + k]));
     return 0;
 }
 
@@ -1051,6 +1114,8 @@ int lumcu_debug_unpack_table(LumcuCtx *c, float *out) {
 int lumcu_wait_idle(LumcuCtx *c) {
     if (int rc = use(c)) return rc;
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->dl_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
     return 0;
 }
 
@@ -1067,6 +1132,13 @@ int lumcu_set_kernel_variant(LumcuCtx *c, int32_t variant) {
     if (!c) return fail(LUMCU_E_ARG, "null context");
     if (variant < 0 || variant > 2) return fail(LUMCU_E_ARG, "unknown kernel variant %d", variant);
     c->kernel_variant = variant;
+    return 0;
+}
+
+int lumcu_set_shard_mode(LumcuCtx *c, int32_t mode) {
+    if (!c) return fail(LUMCU_E_ARG, "null context");
+    if (mode != LUMCU_SHARD_CONTIGUOUS && mode != LUMCU_SHARD_INTERLEAVED) return fail(LUMCU_E_ARG, "unknown shard mode %d", mode);
+    c->shard_chunk = mode == LUMCU_SHARD_INTERLEAVED ? IL_CHUNK : 0;
     return 0;
 }
 

@@ -24,9 +24,12 @@ struct UpdateArgs {
     unsigned long long *__restrict__ dbg_totals;  // S, H
     long long wg_begin;                    // first workgroup of this launch
     long long wg_end;
-    // Interleaved probe sharding (multi-GPU): the range is cut into chunks of il_chunk workgroups and this launch
-    // takes chunks il_rank, il_rank + il_n, ...  il_n == 1: the whole range.  (Every rank then samples every
-    // part of the world, which balances ranks whatever the scene looks like; z-slabs only balance uniform ones.)
+    // Probe sharding (multi-GPU), il_n == 1: the whole range.  il_chunk == 0: CONTIGUOUS -- shard r of n takes
+    // workgroups [T*r/n, T*(r+1)/n) of the range's T (equal probe counts whatever the scene looks like, and each rank
+    // touches only its own part of the world and field: at 8 ranks 4 % faster than dealing chunks out, whose ranks
+    // each pull the whole scene through a cold L2).  il_chunk > 0: INTERLEAVED -- the range is cut into chunks of
+    // il_chunk workgroups and this launch takes chunks il_rank, il_rank + il_n, ... (every rank samples every part of
+    // the world: balances ray LENGTHS too, for scenes whose cost per probe varies by region).
     int il_chunk, il_rank, il_n;
     int time_seed, size, shift;
     int z_begin, z_end;                    // only probes with z in [z_begin,z_end) are processed
@@ -34,18 +37,35 @@ struct UpdateArgs {
     float sun_x, sun_y, sun_z;
 };
 
-// i-th workgroup of this launch -> workgroup index of the dispatch (see UpdateArgs::il_*)
-__device__ __forceinline__ long long il_map(long long wg_begin, int il_chunk, int il_rank, int il_n, long long i) {
-    if (il_n <= 1) return wg_begin + i;
-    const long long c = i / il_chunk;
-    return wg_begin + (c * il_n + il_rank) * il_chunk + (i - c * il_chunk);
+// i-th workgroup of this launch -> workgroup index of the dispatch (see UpdateArgs::il_*).  first = where this launch's
+// window starts (shard_window).  il_chunk == 0: the window is the shard, contiguous.
+__device__ __forceinline__ long long il_map(long long first, int il_chunk, int il_rank, int il_n, long long i) {
+    if (il_n <= 1 || il_chunk == 0) return first + i;
+    const unsigned c = (unsigned)i / (unsigned)il_chunk;           // launch indices fit 32 bits (a 64-bit division per CTA is ~2 % of a trace)
+    return first + ((long long)c * il_n + il_rank) * il_chunk + (long long)((unsigned)i - c * (unsigned)il_chunk);
 }
 
 // last workgroup (exclusive) of this launch: the host's bound, cut down to the device-side request count if there is one
+// (A 64-bit division here cost the C4 update 0.23 ms: it is a ~150-instruction subroutine and every warp of every CTA
+// runs it.  Request counts fit 32 bits -- lumcu_create refuses larger lists -- and size is 1 for a full update.)
+__device__ __forceinline__ long long device_workgroups(const unsigned long long *nreq_dev, int size) {
+    const unsigned n = (unsigned)__ldg(nreq_dev);
+    return (long long)(size == 1 ? n : n / (unsigned)size);
+}
 __device__ __forceinline__ long long dispatch_end(const UpdateArgs &a) {
     long long e = a.wg_end;
-    if (a.nreq_dev) { const long long n = (long long)(__ldg(a.nreq_dev) / (unsigned long long)a.size); e = n < e ? n : e; }
+    if (a.nreq_dev) { const long long n = device_workgroups(a.nreq_dev, a.size); e = n < e ? n : e; }
     return e;
+}
+// The window of the dispatch this launch works in: [wg_begin, dispatch_end), or -- contiguous sharding -- the shard's
+// own part of it, computed here because only the device may know where the dispatch ends.
+struct ShardWindow { long long first, end; };
+__device__ __forceinline__ ShardWindow shard_window(long long wg_begin, long long end, int il_chunk, int il_rank, int il_n) {
+    if (il_n > 1 && il_chunk == 0) {
+        const long long T = end > wg_begin ? end - wg_begin : 0;
+        return {wg_begin + T * il_rank / il_n, wg_begin + T * (il_rank + 1) / il_n};
+    }
+    return {wg_begin, end};
 }
 // a12's store, deferred: the packed texel of workgroup w goes to slot w of every rank's inbox
 __device__ __forceinline__ void stage_word(const UpdateArgs &a, long long w, uint32_t word) {
@@ -66,12 +86,12 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
     __shared__ float sh_light[NSUB][3];
 
     // The grid is capped (a launch must not depend on a request count that only the device knows): CTAs stride.
-    const long long wg_end = dispatch_end(a);
+    const ShardWindow sw = shard_window(a.wg_begin, dispatch_end(a), a.il_chunk, a.il_rank, a.il_n);
     const int ray = threadIdx.x;
     const bool valid = s.brick0_empty && !(__ldg(s.flags) & 1u);        // uniform
     for (long long i = blockIdx.x;; i += gridDim.x) {
-    const long long w = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, i);
-    if (w >= wg_end) return;                                     // uniform per CTA (tail of an interleaved shard)
+    const long long w = il_map(sw.first, a.il_chunk, a.il_rank, a.il_n, i);
+    if (w >= sw.end) return;                                     // uniform per CTA (end of the shard)
     const short4 rq = a.requests[w * (long long)a.size + a.shift];
     if (rq.z < a.z_begin || rq.z >= a.z_end) continue;        // uniform per CTA
     const uint32_t gid_x = (uint32_t)(w * R + ray);
@@ -311,6 +331,7 @@ struct PoolCta {
     short4 req[PPC];
     float sub[PPC * (R < 32 ? 1 : R / 32)][3];   // subgroup means (phase D)
     int next, park[3], chunk;
+    long long wg0;                  // first workgroup of the batch (kept here, not in two registers across the march)
 };
 
 template <int R, int THREADS, int RPT, bool DEBUG, bool FAST>
@@ -326,20 +347,25 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     int &sm_next = cta.next, &sm_chunk = cta.chunk;
     int (&sm_park)[3] = cta.park;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long wg0 = il_map(a.wg_begin, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x * PPC);   // il_chunk % PPC == 0
-    const long long left = dispatch_end(a) - wg0;
-    if (left <= 0) return;                                       // uniform per CTA (tail of an interleaved shard)
-    const int nprobes = left < PPC ? (int)left : PPC;
+    const ShardWindow sw = shard_window(a.wg_begin, dispatch_end(a), a.il_chunk, a.il_rank, a.il_n);
+    int nprobes;
+    {
+        const long long wg0 = il_map(sw.first, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x * PPC);   // il_chunk % PPC == 0
+        const long long left = sw.end - wg0;
+        if (left <= 0) return;                                   // uniform per CTA (end of the shard)
+        nprobes = left < PPC ? (int)left : PPC;
+        for (int i = tid; i < nprobes; i += THREADS) sm_req[i] = a.requests[(wg0 + i) * (long long)a.size + a.shift];
+        if (tid == 0) { sm_next = 0; sm_park[0] = 0; sm_park[1] = 0; sm_park[2] = 0; sm_chunk = 0; cta.wg0 = wg0; }
+    }
     const int nrays = nprobes * R;
-    for (int i = tid; i < nprobes; i += THREADS) sm_req[i] = a.requests[(wg0 + i) * (long long)a.size + a.shift];
-    if (tid == 0) { sm_next = 0; sm_park[0] = 0; sm_park[1] = 0; sm_park[2] = 0; sm_chunk = 0; }
     __syncthreads();
+    const uint32_t gid0 = (uint32_t)(cta.wg0 * R);               // gl_GlobalInvocationID.x of the batch's first ray (mod 2^32, as the shader's uint)
 
     // ---- phase A: setup ----
     for (int r = tid; r < nrays; r += THREADS) {
         const int pr = r / R, ray = r % R;
         const short4 rq = sm_req[pr];
-        const uint32_t gid_x = (uint32_t)((wg0 + pr) * R + ray);
+        const uint32_t gid_x = gid0 + (uint32_t)r;               // = (wg0 + pr) * R + ray
         const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
         f3 o, d, inv;
         setup_ray(rq.x, rq.y, rq.z, gid_x, ray, fib, a.time_seed, o, d, inv);
@@ -389,11 +415,11 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
         c = __shfl_sync(FULL, c, 0);
         if (c >= nrays) break;
         const int r = c + lane;
-        if (r < nrays && sm.done[r]) pool_shade<NR, R, DEBUG, FAST>(sm, s, mc, a, wg0, r, sun, my_s, my_h);
+        if (r < nrays && sm.done[r]) pool_shade<NR, R, DEBUG, FAST>(sm, s, mc, a, cta.wg0, r, sun, my_s, my_h);
     }
     if (warp < tail_warps)                                 // the stragglers, now finished too
         for (int i = tid; i < parked0; i += tail_threads)
-            pool_shade<NR, R, DEBUG, FAST>(sm, s, mc, a, wg0, sm_list[0][i], sun, my_s, my_h);
+            pool_shade<NR, R, DEBUG, FAST>(sm, s, mc, a, cta.wg0, sm_list[0][i], sun, my_s, my_h);
     if constexpr (DEBUG) {
 #pragma unroll
         for (int k = 16; k >= 1; k >>= 1) {
@@ -426,7 +452,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
 #pragma unroll
         for (int g = 0; g < NSUB; g++) { fr += cta.sub[pr * NSUB + g][0]; fg += cta.sub[pr * NSUB + g][1]; fb += cta.sub[pr * NSUB + g][2]; }
         fr /= (float)NSUB; fg /= (float)NSUB; fb /= (float)NSUB;
-        const long long w = wg0 + pr;
+        const long long w = cta.wg0 + pr;
         const short4 rq = sm_req[pr];
         if constexpr (DEBUG) {
             if (a.dbg_pre_blend) {
@@ -497,9 +523,10 @@ __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__re
         }
         __syncthreads();
     }
-    if (nreq_dev) { const long long n = (long long)(*nreq_dev / (unsigned long long)size); wg_end = n < wg_end ? n : wg_end; }
-    long long w = il_map(wg_begin, il.chunk, il.rank, il.n, (long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (w >= wg_end) return;
+    if (nreq_dev) { const long long n = device_workgroups(nreq_dev, size); wg_end = n < wg_end ? n : wg_end; }
+    const ShardWindow sw = shard_window(wg_begin, wg_end, il.chunk, il.rank, il.n);
+    long long w = il_map(sw.first, il.chunk, il.rank, il.n, (long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (w >= sw.end) return;
     short4 rq = requests[w * (long long)size + shift];
     if (rq.z < z_begin || rq.z >= z_end) return;
     if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz)
@@ -537,7 +564,8 @@ __global__ void shift_kernel(uint32_t *__restrict__ field, const uint32_t *__res
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long cells = (long long)wx * wy * wz;
     if (i >= cells) return;
-    int x = (int)(i % wx), y = (int)((i / wx) % wy), z = (int)(i / ((long long)wx * wy));
+    const unsigned row = (unsigned)i / (unsigned)wx;                // cells fit 31 bits
+    int x = (int)((unsigned)i - row * (unsigned)wx), z = (int)(row / (unsigned)wy), y = (int)(row - (unsigned)z * (unsigned)wy);
     int sx = x + dx, sy = y + dy, sz = z + dz;
     if ((unsigned)sx < (unsigned)wx && (unsigned)sy < (unsigned)wy && (unsigned)sz < (unsigned)wz)
         field[i] = tmp[sx + wx * (sy + (long long)wy * sz)];
@@ -590,76 +618,149 @@ __device__ __forceinline__ bool probe_selected(const int16_t *__restrict__ world
     return sum > 0;
 }
 
-// pass 1: per-block counts of selected cells (+ the flag byte per cell)
-__global__ void build_count_kernel(const int16_t *__restrict__ world, int wx, int wy, int wz,
-                                   uint8_t *__restrict__ flags, uint32_t *__restrict__ block_counts) {
-    long long cells = (long long)wx * wy * wz;
-    long long i = (long long)blockIdx.x * BUILD_THREADS + threadIdx.x;
-    bool sel = false;
-    if (i < cells) {
-        int x = (int)(i % wx), y = (int)((i / wx) % wy), z = (int)(i / ((long long)wx * wy));
-        sel = probe_selected(world, wx, wy, wz, x, y, z);
-        flags[i] = sel ? 1 : 0;
-    }
-    int c = __syncthreads_count(sel);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+// ---- the rule-built part of the list in ONE pass ---------------------------------------------------------------
+// Count -> scan -> scatter as three kernels (round 1) spent most of their 114 us (C4 world) between kernels and in a
+// single-CTA scan; one kernel does all three with a decoupled look-back (Merrill & Garland): a CTA takes the next tile of
+// BUILD_TILE consecutive cells (a ticket, so that a tile's predecessors are always already running or done), evaluates
+// the 3x3x3 rule for them, publishes its count, looks back over its predecessors' published counts / prefixes until it
+// knows how many requests precede its tile, publishes its own inclusive prefix and writes its requests -- in cell
+// order, so the list is z,y,x-sorted exactly like the reference's loop produces it.
+// tile_state[t]: bits 63..62 = 0 nothing yet, 1 the tile's own count, 2 the inclusive prefix; bits 61..0 = the number.
+constexpr int BUILD_ITEMS = 4;                                      // x-consecutive cells per thread and group
+constexpr int BUILD_GROUPS = 4;                                     // groups of BUILD_THREADS * BUILD_ITEMS cells per tile
+constexpr int BUILD_GROUP_CELLS = BUILD_THREADS * BUILD_ITEMS;
+constexpr int BUILD_TILE = BUILD_GROUP_CELLS * BUILD_GROUPS;         // 4096 cells: the ticket, the barriers and the look-back
+                                                                    // are paid once per tile, and a CTA lives ~8 us whatever it holds
+// cell index -> (x, y, z); cell indices fit 31 bits (lumcu_create), so 32-bit divisions: the 64-bit ones are ~120-instruction
+// subroutines, and fifteen of them per thread were most of this kernel's first version
+struct Cell3 { int x, y, z; };
+__device__ __forceinline__ Cell3 cell_of(unsigned i, unsigned wx, unsigned wy) {
+    const unsigned row = i / wx, z = row / wy;
+    return {(int)(i - row * wx), (int)(row - z * wy), (int)z};
 }
-
-// pass 2: exclusive scan of the block counts by ONE block (nblocks <= 2^24 handled by looping)
-__global__ void build_scan_kernel(const uint32_t *__restrict__ block_counts, unsigned long long *__restrict__ block_offsets,
-                                  long long nblocks, unsigned long long *__restrict__ total) {
-    __shared__ unsigned long long warp_sums[32];
-    __shared__ unsigned long long carry;
-    if (threadIdx.x == 0) carry = 0;
+__global__ void __launch_bounds__(BUILD_THREADS) build_fused_kernel(const int16_t *__restrict__ world, int wx, int wy, int wz,
+                                                                    uint8_t *__restrict__ flags, unsigned long long *tile_state,
+                                                                    unsigned int *ticket, short4 *__restrict__ out, long long cap,
+                                                                    unsigned long long *__restrict__ total) {
+    __shared__ unsigned int sm_tile;
+    __shared__ int warp_counts[BUILD_GROUPS][BUILD_THREADS / 32];
+    __shared__ unsigned long long sm_part[BUILD_THREADS / 32];
+    __shared__ int sm_stop[BUILD_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) sm_tile = atomicAdd(ticket, 1u);
     __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (long long base = 0; base < nblocks; base += blockDim.x) {
-        long long i = base + threadIdx.x;
-        unsigned long long v = i < nblocks ? block_counts[i] : 0ull, incl = v;
+    const long long tile = sm_tile;
+    const long long cells = (long long)wx * wy * wz, ntiles = (cells + BUILD_TILE - 1) / BUILD_TILE;
+    if (tile >= ntiles) return;
+    // A thread owns, in each of the tile's BUILD_GROUPS groups, BUILD_ITEMS = 4 x-consecutive cells.  Where rows are a
+    // multiple of 4 long the four lie in one row and each of the 9 neighbour rows is one 8-byte load plus the two cells
+    // either side: 27 loads for 4 cells instead of 108, and the sums of the three x-neighbours are shared.  Other
+    // worlds take the cell-by-cell rule.
+    const unsigned uwx = (unsigned)wx, uwy = (unsigned)wy, ucells = (unsigned)cells;
+    const unsigned t0 = (unsigned)tile * BUILD_TILE + (unsigned)tid * BUILD_ITEMS;      // + g * BUILD_GROUP_CELLS
+    unsigned mine = 0;                 // bit 4g + k: cell t0 + g * BUILD_GROUP_CELLS + k is selected
+    int before[BUILD_GROUPS];          // selected cells of the group in front of this thread's (inside its warp, for now)
+#pragma unroll
+    for (int g = 0; g < BUILD_GROUPS; g++) {
+        const unsigned i0 = t0 + g * BUILD_GROUP_CELLS;
+        unsigned m = 0;
+        if (i0 < ucells) {
+            if ((wx & 3) == 0) {
+                const Cell3 c = cell_of(i0, uwx, uwy);
+                int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                const int xl = c.x > 0 ? c.x - 1 : 0, xr = c.x + 4 < wx ? c.x + 4 : wx - 1;
+#pragma unroll
+                for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++) {
+                        const int cy = min(max(c.y + dy, 0), wy - 1), cz = min(max(c.z + dz, 0), wz - 1);
+                        const int16_t *row = world + uwx * ((unsigned)cy + uwy * (unsigned)cz);
+                        const short4 v = __ldg(reinterpret_cast<const short4 *>(row + c.x));
+                        const int l = __ldg(row + xl), r = __ldg(row + xr);
+                        s0 += l + v.x + v.y; s1 += v.x + v.y + v.z; s2 += v.y + v.z + v.w; s3 += v.z + v.w + r;
+                    }
+                m = (s0 > 0 ? 1u : 0u) | (s1 > 0 ? 2u : 0u) | (s2 > 0 ? 4u : 0u) | (s3 > 0 ? 8u : 0u);
+                *reinterpret_cast<uchar4 *>(flags + i0) = make_uchar4(m & 1u, (m >> 1) & 1u, (m >> 2) & 1u, (m >> 3) & 1u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < BUILD_ITEMS; k++) {
+                    const unsigned i = i0 + k;
+                    if (i < ucells) {
+                        const Cell3 c = cell_of(i, uwx, uwy);
+                        const bool sel = probe_selected(world, wx, wy, wz, c.x, c.y, c.z);
+                        flags[i] = sel ? 1 : 0;
+                        m |= sel ? (1u << k) : 0u;
+                    }
+                }
+            }
+        }
+        mine |= m << (4 * g);
+        const int cnt = __popc(m);
+        int incl = cnt;                                             // inclusive scan of the group's counts inside the warp
 #pragma unroll
         for (int k = 1; k < 32; k <<= 1) {
-            unsigned long long n = __shfl_up_sync(0xffffffffu, incl, k);
+            const int n = __shfl_up_sync(0xffffffffu, incl, k);
             if (lane >= k) incl += n;
         }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned long long ws = lane < nw ? warp_sums[lane] : 0ull, wincl = ws;
-#pragma unroll
-            for (int k = 1; k < 32; k <<= 1) {
-                unsigned long long n = __shfl_up_sync(0xffffffffu, wincl, k);
-                if (lane >= k) wincl += n;
-            }
-            warp_sums[lane] = wincl - ws;   // exclusive
-        }
-        __syncthreads();
-        unsigned long long excl = carry + warp_sums[wid] + incl - v;
-        if (i < nblocks) block_offsets[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
+        if (lane == 31) warp_counts[g][wid] = incl;
+        before[g] = incl - cnt;
     }
-    if (threadIdx.x == 0) { total[0] = carry; total[1] = carry; }    // [1]: the rule-built (z-sorted) prefix; specials only grow [0]
-}
-
-// pass 3: ordered scatter (z,y,x order == linear cell order)
-__global__ void build_scatter_kernel(const uint8_t *__restrict__ flags, const unsigned long long *__restrict__ block_offsets,
-                                     int wx, int wy, int wz, short4 *__restrict__ out, long long cap) {
-    __shared__ int warp_counts[BUILD_THREADS / 32];
-    long long cells = (long long)wx * wy * wz;
-    long long i = (long long)blockIdx.x * BUILD_THREADS + threadIdx.x;
-    bool sel = i < cells && flags[i];
-    unsigned b = __ballot_sync(0xffffffffu, sel);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) warp_counts[wid] = __popc(b);
     __syncthreads();
-    int before = 0;
-    for (int k = 0; k < wid; k++) before += warp_counts[k];
-    if (sel) {
-        long long pos = (long long)block_offsets[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
-        if (pos < cap) {
-            int x = (int)(i % wx), y = (int)((i / wx) % wy), z = (int)(i / ((long long)wx * wy));
-            out[pos] = make_short4((short)x, (short)y, (short)z, 0);
+    // rank inside the tile: groups in order, threads in order inside a group, a thread's cells in order
+    int count = 0;
+#pragma unroll
+    for (int g = 0; g < BUILD_GROUPS; g++) {
+        before[g] += count;
+#pragma unroll
+        for (int w = 0; w < BUILD_THREADS / 32; w++) { if (w < wid) before[g] += warp_counts[g][w]; count += warp_counts[g][w]; }
+    }
+    // The whole CTA looks back, BUILD_THREADS tiles per round: thread j reads tile - 1 - j (- BUILD_THREADS per round),
+    // each warp sums the counts of the tiles in front of the nearest one that already knows its inclusive prefix, and
+    // that prefix; the warps' results are combined in order.
+    unsigned long long prefix = 0;
+    {
+        volatile unsigned long long *st = tile_state;
+        const unsigned long long VAL = (1ull << 62) - 1ull;
+        if (tile > 0) {
+            if (tid == 0) st[tile] = (1ull << 62) | (unsigned long long)count;
+            for (long long p0 = tile - 1;; p0 -= BUILD_THREADS) {
+                const long long p = p0 - tid;
+                unsigned long long v = 2ull << 62;                   // in front of tile 0: an inclusive prefix of zero
+                if (p >= 0) while (((v = st[p]) >> 62) == 0) {}
+                const unsigned have = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+                const int stop = have ? __ffs(have) - 1 : 32;          // the nearest tile with a prefix ends the walk
+                unsigned long long part = lane <= stop ? (v & VAL) : 0ull;
+#pragma unroll
+                for (int k = 16; k >= 1; k >>= 1) part += __shfl_xor_sync(0xffffffffu, part, k);
+                __syncthreads();                                     // (sm_part / sm_stop of the previous round have been read)
+                if (lane == 0) { sm_part[wid] = part; sm_stop[wid] = stop; }
+                __syncthreads();
+                bool found = false;
+#pragma unroll
+                for (int w = 0; w < BUILD_THREADS / 32; w++)
+                    if (!found) { prefix += sm_part[w]; found = sm_stop[w] < 32; }
+                if (found) break;                                    // uniform: every thread read the same arrays
+            }
+        }
+        if (tid == 0) {
+            st[tile] = (2ull << 62) | (prefix + (unsigned long long)count);
+            if (tile == ntiles - 1) { total[0] = prefix + (unsigned long long)count; total[1] = total[0]; }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < BUILD_GROUPS; g++) {
+        const unsigned m = (mine >> (4 * g)) & 15u;
+        if (m) {
+            long long pos = (long long)prefix + before[g];
+            Cell3 c = cell_of(t0 + g * BUILD_GROUP_CELLS, uwx, uwy);
+#pragma unroll
+            for (int k = 0; k < BUILD_ITEMS; k++) {
+                if ((m >> k) & 1u) {
+                    if (pos < cap) out[pos] = make_short4((short)c.x, (short)c.y, (short)c.z, 0);
+                    pos++;
+                }
+                if (++c.x >= wx) { c.x = 0; if (++c.y >= wy) { c.y = 0; c.z++; } }      // the next cell: carry into y, z
+            }
         }
     }
 }

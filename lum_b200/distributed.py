@@ -8,9 +8,9 @@ their slabs -- either with ONE in-place all-gather (all_gather_field), or fused 
 lumcu_update_slab_exchange stores every new texel straight into all ranks' field replicas over NVLink
 peer memory between two flag barriers (open_peer_exchange wires it) -- after which every rank holds the
 identical new field for the next frame's gathers.  With the fused exchange a rank's texels need not be contiguous
-in the field, so the default sharding there is INTERLEAVED (lumcu_update_shard_exchange): the dispatch's
-workgroups are dealt to the ranks in chunks of SHARD_CHUNK, which balances the ranks whatever the scene looks
-like (z-slabs only balance uniform scenes; the demo world is all ground).  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
+in the field, so the sharding there is by workgroup index (lumcu_update_shard_exchange): CONTIGUOUS equal ranges of
+the dispatch by default (equal probe counts whatever the scene looks like; each rank touches only its part of the
+world), or INTERLEAVED chunks of SHARD_CHUNK (lumcu_set_shard_mode), which also balance the cost per probe.  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
 CPU for the tests of this host-side logic).
 """
 from __future__ import annotations
@@ -20,15 +20,20 @@ SHARD_CHUNK = 3072      # = IL_CHUNK of csrc/lumcu.cu: a multiple of every poole
 
 
 def shard_workgroups(nwg: int, rank: int, world_size: int, chunk: int = SHARD_CHUNK):
-    """Workgroup indices of [0, nwg) that interleaved shard `rank` of `world_size` owns, in the order the
-    kernels visit them: chunk c of the dispatch belongs to rank c % world_size (lumcu_update_shard)."""
+    """Workgroup indices of [0, nwg) that shard `rank` of `world_size` owns, in the order the kernels visit them
+    (lumcu_update_shard).  chunk > 0 (LUMCU_SHARD_INTERLEAVED): chunk c of the dispatch belongs to rank
+    c % world_size.  chunk == 0 (LUMCU_SHARD_CONTIGUOUS, the stage's default): [nwg*rank/n, nwg*(rank+1)/n)."""
     import numpy as np
     w = np.arange(nwg, dtype=np.int64)
+    if chunk == 0:
+        return w[nwg * rank // world_size: nwg * (rank + 1) // world_size]
     return w[(w // chunk) % world_size == rank]
 
 
 def shard_count(nwg: int, rank: int, world_size: int, chunk: int = SHARD_CHUNK) -> int:
     """len(shard_workgroups(...)) in closed form (what sizes the shard's launches)."""
+    if chunk == 0:
+        return nwg * (rank + 1) // world_size - nwg * rank // world_size
     full, rem = divmod(nwg, chunk)
     return (full // world_size) * chunk + (chunk if full % world_size > rank else 0) + (rem if full % world_size == rank else 0)
 

@@ -29,7 +29,7 @@ static long long trace_on_host(int wx, int wy, int wz, int capacity, int brick0_
                                const float *table, const float *sun3, int variant, Interleave il, uint32_t *staged,
                                float *pre_blend, uint32_t *ray_samples, uint8_t *ray_hits, unsigned long long *totals,
                                const PeerWords *inbox = nullptr, long long slack = 0) {
-    if (size < 1 || shift < 0 || shift >= size || il.n < 1 || il.rank < 0 || il.rank >= il.n || il.chunk < 1) return -1;
+    if (size < 1 || shift < 0 || shift >= size || il.n < 1 || il.rank < 0 || il.rank >= il.n || il.chunk < 0) return -1;
     std::vector<float4> mat4(256);
     for (int i = 0; i < 256; i++) mat4[i] = make_float4(materials[6 * i], materials[6 * i + 1], materials[6 * i + 2], materials[6 * i + 4]);
     const long long cells = (long long)wx * wy * wz;
@@ -56,7 +56,9 @@ static long long trace_on_host(int wx, int wy, int wz, int capacity, int brick0_
     totals[0] = totals[1] = 0;
     // workgroups this launch traces (lumcu.cu: il_count)
     long long nwg = nwg_all;
-    if (il.n > 1) {
+    if (il.n > 1 && il.chunk == 0) {
+        nwg = (nwg_all + il.n - 1) / il.n;         // contiguous shards: sized for the largest
+    } else if (il.n > 1) {
         const long long full = nwg_all / il.chunk, rem = nwg_all % il.chunk;
         nwg = (full / il.n) * il.chunk + ((full % il.n) > il.rank ? il.chunk : 0) + ((full % il.n) == il.rank ? rem : 0);
     }
@@ -160,22 +162,22 @@ extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capaci
     return status ? -2 : 0;
 }
 
-// The request-list builder as lumcu_build_requests launches it: count -> scan -> ordered scatter (-> specials).
-// out: int16 [cap][4]; returns the request count, *nbuilt = the z-sorted part (without the special tail).
-// (The two single-CTA kernels run with 256 instead of 1024 threads here -- they are written for any multiple of 32 --
-// to keep the emulator at 256 OS threads.)
+// The request-list builder as lumcu_build_requests launches it: build_fused_kernel (rule + look-back scan + ordered
+// scatter in one pass; the emulator runs CTAs one after another, so a tile's predecessors have always published) and
+// build_specials_kernel.  out: int16 [cap][4]; returns the request count, *nbuilt = the z-sorted part (without the
+// special tail).  (The single-CTA specials kernel runs with 256 instead of 1024 threads here -- it is written for any
+// multiple of 32 -- to keep the emulator at 256 OS threads.)
 extern "C" long long kernels_on_host_build_requests(int wx, int wy, int wz, const int16_t *world, const int16_t *special,
                                                     int nspecial, int16_t *out, long long cap, long long *nbuilt) {
     const long long cells = (long long)wx * wy * wz;
-    const long long nblocks = (cells + BUILD_THREADS - 1) / BUILD_THREADS;
+    const long long ntiles = (cells + BUILD_TILE - 1) / BUILD_TILE;
     std::vector<uint8_t> flags((size_t)cells);
-    std::vector<uint32_t> counts((size_t)nblocks);
-    std::vector<unsigned long long> offsets((size_t)nblocks);
+    std::vector<unsigned long long> state((size_t)ntiles + 1, 0ull);
     unsigned long long total[2] = {0, 0};      // [0] the list, [1] its rule-built prefix
     short4 *o = reinterpret_cast<short4 *>(out);
-    emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_count_kernel(world, wx, wy, wz, flags.data(), counts.data()); });
-    emu_launch(1, 1, 256, [&] { build_scan_kernel(counts.data(), offsets.data(), nblocks, total); });
-    emu_launch((unsigned)nblocks, 1, BUILD_THREADS, [&] { build_scatter_kernel(flags.data(), offsets.data(), wx, wy, wz, o, cap); });
+    emu_launch((unsigned)ntiles, 1, BUILD_THREADS, [&] {
+        build_fused_kernel(world, wx, wy, wz, flags.data(), state.data(), reinterpret_cast<unsigned int *>(state.data() + ntiles), o, cap, total);
+    });
     if (nspecial > 0)
         emu_launch(1, 1, 256, [&] {
             build_specials_kernel(flags.data(), wx, wy, wz, reinterpret_cast<const short4 *>(special), nspecial, o, total, cap);

@@ -115,6 +115,7 @@ static inline void __threadfence_system() { __sync_synchronize(); }
 static inline void __threadfence() { __sync_synchronize(); }
 static inline long long clock64() { return 0; }
 static inline void __nanosleep(unsigned) {}
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <class T> static inline T __ldcv(const T *p) { return *(const volatile T *)p; }
 using std::max;
 using std::min;

@@ -35,6 +35,8 @@ def test_interleaved_shard_arithmetic(nwg, world):
     for r in range(world):
         idx = D.shard_workgroups(nwg, r, world)
         assert len(idx) == D.shard_count(nwg, r, world)
+        cont = D.shard_workgroups(nwg, r, world, 0)                    # LUMCU_SHARD_CONTIGUOUS
+        assert len(cont) == D.shard_count(nwg, r, world, 0) and (len(cont) == 0 or (np.diff(cont) == 1).all())
         assert np.all(np.diff(idx) > 0)
         seen[idx] += 1
     assert np.all(seen == 1)

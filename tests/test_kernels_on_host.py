@@ -143,8 +143,9 @@ def test_fuzz_worlds_kernels(emu, oracle_mod, case):
 
 
 def test_request_builder_kernels(emu, oracle_mod, demo):
-    """SURVEY a13 on the emulator: build_count / build_scan / build_scatter / build_specials against the oracle's list
-    (demo world: 2,689 requests in z,y,x order; specials appended in submission order unless already selected)."""
+    """SURVEY a13 on the emulator: build_fused_kernel (rule, look-back scan over 36 tiles, ordered scatter) and
+    build_specials_kernel against the oracle's list (demo world: 2,689 requests in z,y,x order; specials appended in
+    submission order unless already selected)."""
     O = oracle_mod
     emu.kernels_on_host_build_requests.restype = C.c_longlong
     world = np.ascontiguousarray(demo["world"], np.int16)
@@ -163,6 +164,27 @@ def test_request_builder_kernels(emu, oracle_mod, demo):
         assert nbuilt.value == 2689
         assert n == len(ref)
         assert np.array_equal(out[:n], ref)
+
+
+@pytest.mark.parametrize("dims,density", [((37, 11, 9), 0.02), ((64, 33, 5), 0.004), ((4, 4, 1), 0.5), ((1, 1, 1), 1.0),
+                                          ((130, 3, 7), 0.3), ((256, 12, 3), 0.0)])
+def test_request_builder_shapes(emu, oracle_mod, dims, density):
+    """Rows that are / are not a multiple of four cells long (the 8-byte row loads vs the cell-by-cell rule), a
+    ragged last tile, worlds smaller than a tile, negative ids (they lower the neighbourhood sum), an empty world."""
+    O = oracle_mod
+    emu.kernels_on_host_build_requests.restype = C.c_longlong
+    wx, wy, wz = dims
+    rng = np.random.default_rng(wx * 1000 + wy)
+    world = np.where(rng.random((wz, wy, wx)) < density, rng.integers(-2, 30, (wz, wy, wx)), 0).astype(np.int16)
+    sp = np.array([(int(rng.integers(0, wx)), int(rng.integers(0, wy)), int(rng.integers(0, wz)), 0) for _ in range(9)], np.int16)
+    out = np.zeros((world.size + len(sp), 4), np.int16)
+    nbuilt = C.c_longlong(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = emu.kernels_on_host_build_requests(C.c_int(wx), C.c_int(wy), C.c_int(wz), p(world), p(sp), C.c_int(len(sp)),
+                                           p(out), C.c_longlong(len(out)), C.byref(nbuilt))
+    ref = O.build_requests(world, sp)
+    assert nbuilt.value == len(O.build_requests(world))
+    assert n == len(ref) and np.array_equal(out[:n], ref)
 
 
 @pytest.mark.parametrize("d", [(1, 0, 0), (0, -2, 1), (-3, 4, -1), (0, 0, 0), (48, 0, 0)])
@@ -231,8 +253,9 @@ def test_slab_bound_kernel(emu, oracle_mod, demo):
             assert (int(out[0]), int(out[1])) == (int(np.searchsorted(zs, zb, "left")), int(np.searchsorted(zs, ze, "left")))
 
 
+@pytest.mark.parametrize("chunk", [12, 0], ids=["interleaved", "contiguous"])
 @pytest.mark.parametrize("nranks,variant", [(2, POOL), (3, POOL), (2, WG)])
-def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant):
+def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant, chunk):
     """SURVEY 8e on the emulator: three frames dealt to `nranks` ranks in interleaved chunks (il_map in the kernels), every
     rank's texels stored into every rank's inbox from the trace kernel (alternating halves), arrive_kernel, then each rank's
     commit_kernel behind the flag wait -- all replicas equal the single-device field after every frame."""
@@ -254,7 +277,7 @@ def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nrank
     emu.kernels_on_host_update_sharded.restype = C.c_int
     rc = emu.kernels_on_host_update_sharded(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]), C.c_int(1),
                                             C.c_int(64), C.c_float(0.01), p(world), p(bricks), p(mats), p(replicas),
-                                            C.c_int(nranks), C.c_int(12), p(req), C.c_longlong(len(req)), C.c_int(4),
+                                            C.c_int(nranks), C.c_int(chunk), p(req), C.c_longlong(len(req)), C.c_int(4),
                                             C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant), C.c_int(3))
     assert rc == 0
     for r in range(nranks):

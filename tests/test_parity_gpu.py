@@ -317,8 +317,9 @@ def test_ranges_and_slabs_compose(oracle_mod, demo):
     assert st.slab_range(1, 0, 4, 8) == (int(np.searchsorted(zs[:prefix], 4)), int(np.searchsorted(zs[:prefix], 8)))
 
 
+@pytest.mark.parametrize("mode", ["contiguous", "interleaved"])
 @pytest.mark.parametrize("nranks", [2, 3, 8])
-def test_interleaved_shards_compose(oracle_mod, nranks):
+def test_interleaved_shards_compose(oracle_mod, nranks, mode):
     """lumcu_update_shard: chunks of 3072 workgroups dealt round-robin to the ranks.  Each shard, run from the
     same starting field, must change exactly its own probes' texels to the oracle's values; together they make
     the full update.  The world is large enough for several chunks per rank and a ragged last chunk, and for
@@ -335,9 +336,12 @@ def test_interleaved_shards_compose(oracle_mod, nranks):
     ref = O.update(sc, f0, req, 5)["field"]
     cell = req[:, 0].astype(np.int64) + 40 * (req[:, 1].astype(np.int64) + 36 * req[:, 2].astype(np.int64))
     from lum_b200 import distributed as D
-    owner = np.empty(n, np.int64)
+    import lum_b200
+    st.set_shard_mode(lum_b200.SHARD_INTERLEAVED if mode == "interleaved" else lum_b200.SHARD_CONTIGUOUS)
+    owner = np.full(n, -1, np.int64)
     for r in range(nranks):
-        owner[D.shard_workgroups(n, r, nranks)] = r
+        owner[D.shard_workgroups(n, r, nranks, D.SHARD_CHUNK if mode == "interleaved" else 0)] = r
+    assert (owner >= 0).all()
     for variant in (1, 0):                     # pooled and per-workgroup kernel: both map launch index -> workgroup
         st.set_kernel_variant(variant)
         union = f0.copy()
