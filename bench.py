@@ -223,13 +223,39 @@ class Runner:
         so the copies of one frame overlap the tracing of its neighbours.  Everything is inside the timed region."""
         slot = seed & 1
         self.st.wait_fence(slot)                              # the frame that last used this result buffer is done
+        self._mark()
         self.st.upload_world_async(self.world_host)           # H2D
+        self._mark()
         self.st.build_requests(sync=False)
+        self._mark()
         self.step_resident(seed)
+        self._mark()
         lo, hi = (self.rank * self.slab_cells, (self.rank + 1) * self.slab_cells) if self.n > 1 else (0, self.cells)
         self.st.download_field_async(self.field_host2[slot][lo:hi], lo, hi - lo)      # D2H
         self.st.record_fence(slot)
+        self._mark()
         return self.field_host2[slot][lo:hi]
+
+    phase_events = None
+
+    def _mark(self):
+        if self.phase_events is not None:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record(self.stream)
+            self.phase_events.append(e)
+
+    def phase_breakdown(self):
+        """ms on the stage's stream between the marks of step_e2e (mean over the steps of the last diagnostic loop):
+        [world upload seen by the stream, request build, update (+ exchange), after the download was queued]."""
+        ev = self.phase_events or []
+        n = len(ev) // 5
+        if n < 2:
+            return None
+        out = np.zeros(4)
+        for k in range(1, n):                      # skip the first step (nothing to overlap with)
+            for j in range(4):
+                out[j] += ev[5 * k + j].elapsed_time(ev[5 * k + j + 1])
+        return [float(v / (n - 1)) for v in out]
 
     def drain(self):
         self.st.wait_fence(0); self.st.wait_fence(1)
@@ -354,17 +380,27 @@ def measure(runner, steps, warmup, peak):
             ks.append(st.last_kernel_ms())
     st.set_profiling(False)
     kernel_ms = float(np.mean(ks))
+    kernel_ms_ranks = [kernel_ms]
+    if runner.n > 1:                                          # how evenly the shards load the ranks
+        t = runner.torch.tensor([kernel_ms], dtype=runner.torch.float64, device=runner.field_t.device)
+        out = [runner.torch.empty_like(t) for _ in range(runner.n)]
+        runner.dist.all_gather(out, t)
+        kernel_ms_ranks = [float(o.item()) for o in out]
     ab = runner.algorithmic_bytes(steps, warmup)
     alg_bytes = float(np.mean(ab))
     kt = kernel_ms if kernel_ms else ms_per_step
     achieved = alg_bytes / (kt * 1e-3) / 1e9
     # end to end
     e2e_ms, _ = runner.timed(runner.step_e2e, steps, warmup, span=True)
+    runner.phase_events = []
+    span_ms, _ = runner.timed(runner.step_e2e, steps, 1, span=True)
+    phases = runner.phase_breakdown()
+    runner.phase_events = None
     e2e_value = total_rays / (e2e_ms / steps * 1e-3)
     world_bytes = runner.world_host.nbytes
-    return dict(value=value, ms_per_step=ms_per_step, per_step_ms=per, kernel_ms=kernel_ms,
+    return dict(value=value, ms_per_step=ms_per_step, per_step_ms=per, kernel_ms=kernel_ms, kernel_ms_ranks=kernel_ms_ranks,
                 alg_bytes=alg_bytes, achieved=achieved, frac=achieved / peak,
-                e2e_value=e2e_value, e2e_ms=e2e_ms / steps, h2d=world_bytes * runner.n,      # every rank uploads the world
+                e2e_phases=phases, e2e_value=e2e_value, e2e_ms=e2e_ms / steps, h2d=world_bytes * runner.n,      # every rank uploads the world
                 d2h=runner.cells * 4 // runner.n * runner.n, launches=launches_timed,       # each rank reads its slab back
                 probes=runner.nreq, rays=total_rays)
 
@@ -566,6 +602,7 @@ def roofline_object(workload, world_size, rays, m, peak, peak_src, scene, runner
     ro = {"bound": "hbm", "achieved": m["achieved"], "peak": peak, "unit": "GB/s", "frac": m["frac"],
           "traffic": ev.get("dram_bytes_per_launch"), "peak_source": peak_src,
           "kernel": KERNEL_NAMES[pooled].format(r=rays, t=256 if rays == 256 else 128), "kernel_ms": m["kernel_ms"],
+          "kernel_ms_per_rank": m["kernel_ms_ranks"],
           "algorithmic_bytes_per_launch": m["alg_bytes"],
           # SURVEY 8d's second figure: what one update must touch at least once
           "compulsory_unique_bytes": int(scene["world"].nbytes + scene["bricks"].nbytes + 6144 + 2 * runner.cells * 4)}
@@ -592,6 +629,8 @@ def run_ours(args, rank, local_rank, world_size):
     scene = make_scene(args.workload)
     rays = args.rays_per_probe
     runner = Runner(scene, local_rank, rank, world_size, torch, dist, exchange=args.exchange, rays=rays)
+    import lum_b200
+    runner.st.set_shard_mode(lum_b200.SHARD_INTERLEAVED if args.shard_mode == "interleaved" else lum_b200.SHARD_CONTIGUOUS)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -634,12 +673,13 @@ def run_ours(args, rank, local_rank, world_size):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": rays,
-                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + ("contiguous equal ranges of the dispatch; the trace kernel stores each new texel into every rank's inbox over NVLink, one flag barrier, local commit"
+                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + (("contiguous equal ranges of the dispatch" if args.shard_mode == "contiguous" else "interleaved chunks of 3072 workgroups") + "; one flag barrier per frame, then one kernel reads every texel from its owner's staging array over NVLink and commits it locally"
                                                                              if runner.fused else "z-slabs + NCCL field all-gather"))
                            if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
                            "time_seed": "step index", "initial_field": "zero"},
                 "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"],
-                        "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+                        "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                        "frames_in_flight": 2, "stream_ms_upload_build_update_download": m["e2e_phases"]},
                 "gpu_launches": m["launches"],
                 "roofline": roofline_object(args.workload, world_size, rays, m, peak, peak_src, scene, runner),
                 "clocks": clocks}
@@ -666,6 +706,8 @@ def main():
                     help="N>1: how the ranks exchange their slabs of the field each step")
     ap.add_argument("--rays-per-probe", type=int, default=64, choices=[16, 32, 64, 128, 256],
                     help="BASELINE configs[4] sweeps 16-256 (the reference only defines 64); the demo / config-3 / glossy lines need 64")
+    ap.add_argument("--shard-mode", default="interleaved", choices=["contiguous", "interleaved"],
+                    help="N>1, fused exchange: how the dispatch's workgroups are dealt to the ranks (lumcu_set_shard_mode)")
     ap.add_argument("--no-demo", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--api-config3", action="store_true", help=argparse.SUPPRESS)

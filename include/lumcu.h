@@ -142,11 +142,13 @@ int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, i
                                int32_t z_begin, int32_t z_end);
 /* Probe sharding by workgroup index (no z-sorted list needed).  lumcu_set_shard_mode chooses how the dispatch's
  * workgroups are dealt to `nranks` shards:
- *   LUMCU_SHARD_CONTIGUOUS (default)  shard r takes workgroups [T*r/n, T*(r+1)/n) of the dispatch's T: equal probe
- *       counts whatever the scene looks like, and each rank touches only its own part of world and field;
- *   LUMCU_SHARD_INTERLEAVED           the dispatch is cut into chunks of 3072 workgroups and shard r takes chunks
- *       r, r + n, ...: every rank samples every part of the world, which also balances the COST per probe when that
- *       varies by region, at the price of every rank pulling the whole scene through its caches.
+ *   LUMCU_SHARD_INTERLEAVED (default) the dispatch is cut into chunks of 3072 workgroups and shard r takes chunks
+ *       r, r + n, ...: every rank samples every part of the world, so the ranks finish together whatever the scene looks
+ *       like (C4 at 8 ranks: all trace kernels within 0.7 % of each other);
+ *   LUMCU_SHARD_CONTIGUOUS            shard r takes workgroups [T*r/n, T*(r+1)/n) of the dispatch's T: equal probe
+ *       counts, and each rank touches only its own part of world and field (the first rank is 2 % faster for it) --
+ *       but the cost per probe varies with height even in the uniform C4 world (ground below, sky above: the middle
+ *       ranks take 3 % longer than the first), and the frame waits for the slowest rank.
  * Both need the texel-wise exchange (a shard's texels are not a slab of the field).  lumcu_update_shard: trace + local
  * commit of one shard (the union over all shards, each from the same starting field, equals lumcu_update).
  * lumcu_update_shard_exchange: the per-frame call of step 4 above (rank and nranks as given to lumcu_peers_open). */

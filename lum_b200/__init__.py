@@ -353,7 +353,7 @@ class RadianceStage:
         self._ck(self.lib.lumcu_set_kernel_variant(self.ctx, int(variant)))
 
     def set_shard_mode(self, mode):
-        """SHARD_CONTIGUOUS (default) or SHARD_INTERLEAVED (lumcu_set_shard_mode)."""
+        """SHARD_INTERLEAVED (default) or SHARD_CONTIGUOUS (lumcu_set_shard_mode)."""
         self._ck(self.lib.lumcu_set_shard_mode(self.ctx, int(mode)))
 
     def set_profiling(self, on):

@@ -73,6 +73,9 @@ struct Staging {
 
 }  // namespace
 
+// Interleaved sharding (UpdateArgs::il_*): chunk is a multiple of every pooled kernel's probes-per-CTA.
+constexpr int IL_CHUNK = 3072;
+
 struct LumcuCtx {
     LumcuDesc desc{};
     int wx = 0, wy = 0, wz = 0, R = 64;
@@ -112,7 +115,7 @@ struct LumcuCtx {
     int sm_count = 148;          // cudaDevAttrMultiProcessorCount (grid sizing of the grid-stride kernels)
     int pool_threads = 128;      // tuning knobs (env LUMCU_POOL_THREADS / LUMCU_CARVEOUT, read at create)
     int carveout = -1;
-    int shard_chunk = 0;         // lumcu_set_shard_mode: 0 = contiguous shards (default), IL_CHUNK = interleaved chunks
+    int shard_chunk = IL_CHUNK;  // lumcu_set_shard_mode: IL_CHUNK = interleaved chunks (default), 0 = contiguous shards
     int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
     bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
     uint32_t *d_scene_flags = nullptr;     // bit 0: world ids outside the palette (validate_world_kernel)
@@ -194,9 +197,6 @@ void host_direction_table(int n, std::vector<float> &out) {
         out[3 * k + 2] = ct;
     }
 }
-
-// Interleaved sharding (UpdateArgs::il_*): chunk is a multiple of every pooled kernel's probes-per-CTA.
-constexpr int IL_CHUNK = 3072;
 
 // production path: pooled kernel (no z filter); one CTA per RPT*threads rays
 #ifndef LUMCU_RPT
@@ -476,7 +476,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     if (const char *e = getenv("LUMCU_POOL_THREADS")) c->pool_threads = atoi(e) == 256 ? 256 : 128;
     if (const char *e = getenv("LUMCU_CARVEOUT")) c->carveout = atoi(e);
     if (const char *e = getenv("LUMCU_KERNEL_VARIANT")) c->kernel_variant = atoi(e);
-    if (const char *e = getenv("LUMCU_SHARD_MODE")) c->shard_chunk = atoi(e) == LUMCU_SHARD_INTERLEAVED ? IL_CHUNK : 0;
+    if (const char *e = getenv("LUMCU_SHARD_MODE")) c->shard_chunk = atoi(e) == LUMCU_SHARD_CONTIGUOUS ? 0 : IL_CHUNK;
     host_direction_table(R, c->h_table);
     CUB(cudaMemcpyAsync(c->d_table, c->h_table.data(), (size_t)R * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     {   // normalize(vec3(0.5,0.5,-0.9)) (radiance.comp:42), f32, x->y->z dot
@@ -953,27 +953,42 @@ int lumcu_update_shard(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shi
     return 0;
 }
 
-// One multi-GPU frame (epoch e, parity = e & 1):
-//   trace     this rank's workgroups; the new texels go straight into half `parity` of EVERY rank's staged[] (its
-//             inbox) from the kernel's last phase -- peer stores over NVLink, spread over the whole trace;
+// One multi-GPU frame (epoch e, parity = e & 1), workgroup shards:
+//   trace     this rank's workgroups into half `parity` of its own staged[] -- nothing remote;
 //   arrive    a one-warp kernel: system fence, then e into every rank's flag array;
-//   commit    waits (inside the kernel) until every rank has arrived at e, then scatters the whole dispatch from the
-//             local inbox into the local field.  Nothing remote is read or written here.
-// One barrier per frame.  The next frame's trace reads only local memory (stream order suffices) and writes the other
-// half of the inboxes; a rank can be writing half p of a peer's inbox again (epoch e + 2) only after the barrier of
-// epoch e + 1, which that peer reaches after its commit of epoch e -- the last reader of half p -- in stream order.
+//   gather + commit   one persistent kernel: waits (inside) until every rank has arrived at e, then reads the texel of
+//             every workgroup of the dispatch from its owner's staged[] (NVLink, full lines) and stores it into the
+//             local field.
+// One barrier per frame, no collective call.  The next frame's trace reads only local memory (stream order suffices)
+// and writes the other half of staged[]; a rank overwrites half p again (epoch e + 2) only after the barrier of epoch
+// e + 1, which every peer reaches after its gather of epoch e -- the last reader of half p -- in stream order.
+// (z-slabs, lumcu_update_slab_exchange: the same frame with the transfer as a PUSH from the trace kernel's last phase
+// into every rank's inbox, and a local commit behind the wait.)
 static int exchange_frame(LumcuCtx *c, int time_seed, int size, int shift, long long b, long long e, bool slab,
                           int z_begin, int z_end, Interleave il) {
     const long long nwg_all = c->nreq / size, tail = slab ? sorted_workgroups(c, size, shift) : nwg_all;
     c->epoch++;
     const int parity = (int)(c->epoch & 1u);
-    const PeerWords *inbox = &c->peer_inbox[parity];
+    // z-slabs PUSH (the trace stores into every rank's inbox: a slab's owner is not a function of the workgroup index);
+    // workgroup shards PULL (gather_commit_kernel reads each texel from its owner's staged[])
+    const PeerWords *inbox = slab ? &c->peer_inbox[parity] : nullptr;
     CU(cudaEventRecord(c->ev_begin, c->stream));
     if (int rc = do_update(c, time_seed, size, shift, b, e, -32768, 32768, false, il, false, inbox, parity)) return rc;
     if (slab && tail < nwg_all)      // unsorted tail (specials): every rank scans it, keeps its slab's probes
         if (int rc = do_update(c, time_seed, size, shift, tail, nwg_all, z_begin, z_end, false, Interleave{IL_CHUNK, 0, 1}, true, inbox, parity)) return rc;
     if (int rc = arrive(c)) return rc;
-    if (int rc = commit_local(c, size, shift, 0, nwg_all, -32768, 32768, Interleave{IL_CHUNK, 0, 1}, parity, exchange_wait(c))) return rc;
+    if (slab) {
+        if (int rc = commit_local(c, size, shift, 0, nwg_all, -32768, 32768, Interleave{IL_CHUNK, 0, 1}, parity, exchange_wait(c))) return rc;
+    } else if (nwg_all > 0) {
+        if (int rc = before_field_write(c)) return rc;
+        const ShardSources src{c->peer_inbox[parity], il.chunk, il.n};
+        const int ct = 256;
+        const long long blocks = std::min<long long>((nwg_all + ct - 1) / ct, (long long)c->sm_count * 8);
+        gather_commit_kernel<<<(unsigned)blocks, ct, 0, c->stream>>>(c->d_field, src, c->d_requests, 0, nwg_all, size, shift,
+                                                                    c->wx, c->wy, c->wz, count_ptr(c), exchange_wait(c));
+        c->launches++;
+        CU(cudaGetLastError());
+    }
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;

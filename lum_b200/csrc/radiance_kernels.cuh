@@ -57,13 +57,24 @@ __device__ __forceinline__ long long dispatch_end(const UpdateArgs &a) {
     if (a.nreq_dev) { const long long n = device_workgroups(a.nreq_dev, a.size); e = n < e ? n : e; }
     return e;
 }
+// Does where this launch's window STARTS depend on the device-side count?  Only a contiguous split does (its shard
+// boundaries are fractions of the dispatch's length).  Everywhere else a CTA knows its first workgroup from the launch
+// arguments alone and can fetch its requests while the count is still on its way: the count is a global load at the very
+// start of every CTA, and waiting for it before anything else cost the C4 update 0.13 ms.
+__device__ __forceinline__ bool window_needs_count(const UpdateArgs &a) { return a.nreq_dev && a.il_n > 1 && a.il_chunk == 0; }
 // The window of the dispatch this launch works in: [wg_begin, dispatch_end), or -- contiguous sharding -- the shard's
 // own part of it, computed here because only the device may know where the dispatch ends.
 struct ShardWindow { long long first, end; };
+// floor(T * r / n) for T < 2^32, r <= n <= 16, in 32-bit arithmetic (every thread of every CTA evaluates this, and a
+// 64-bit division is a ~120-instruction subroutine): T = q*n + m  =>  T*r/n = q*r + m*r/n.
+__device__ __forceinline__ long long split_point(unsigned T, unsigned r, unsigned n) {
+    const unsigned q = T / n, m = T - q * n;
+    return (long long)q * r + (m * r) / n;
+}
 __device__ __forceinline__ ShardWindow shard_window(long long wg_begin, long long end, int il_chunk, int il_rank, int il_n) {
     if (il_n > 1 && il_chunk == 0) {
-        const long long T = end > wg_begin ? end - wg_begin : 0;
-        return {wg_begin + T * il_rank / il_n, wg_begin + T * (il_rank + 1) / il_n};
+        const unsigned T = end > wg_begin ? (unsigned)(end - wg_begin) : 0u;
+        return {wg_begin + split_point(T, (unsigned)il_rank, (unsigned)il_n), wg_begin + split_point(T, (unsigned)il_rank + 1u, (unsigned)il_n)};
     }
     return {wg_begin, end};
 }
@@ -86,13 +97,16 @@ __global__ void __launch_bounds__(R) radiance_update_wg_kernel(SceneView s, Upda
     __shared__ float sh_light[NSUB][3];
 
     // The grid is capped (a launch must not depend on a request count that only the device knows): CTAs stride.
-    const ShardWindow sw = shard_window(a.wg_begin, dispatch_end(a), a.il_chunk, a.il_rank, a.il_n);
     const int ray = threadIdx.x;
+    // the window from the host's bound first (no wait for the device-side count unless its start depends on it) ...
+    ShardWindow sw = shard_window(a.wg_begin, window_needs_count(a) ? dispatch_end(a) : a.wg_end, a.il_chunk, a.il_rank, a.il_n);
     const bool valid = s.brick0_empty && !(__ldg(s.flags) & 1u);        // uniform
     for (long long i = blockIdx.x;; i += gridDim.x) {
     const long long w = il_map(sw.first, a.il_chunk, a.il_rank, a.il_n, i);
     if (w >= sw.end) return;                                     // uniform per CTA (end of the shard)
-    const short4 rq = a.requests[w * (long long)a.size + a.shift];
+    const short4 rq = a.requests[w * (long long)a.size + a.shift];     // (inside max_requests even beyond the real count)
+    // ... and the real end once the request is on its way
+    if (i == (long long)blockIdx.x && !window_needs_count(a)) { const long long e = dispatch_end(a); sw.end = e < sw.end ? e : sw.end; if (w >= sw.end) return; }
     if (rq.z < a.z_begin || rq.z >= a.z_end) continue;        // uniform per CTA
     const uint32_t gid_x = (uint32_t)(w * R + ray);
     const f3 fib = {__ldg(a.dir_table + 3 * ray), __ldg(a.dir_table + 3 * ray + 1), __ldg(a.dir_table + 3 * ray + 2)};
@@ -347,14 +361,21 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     int &sm_next = cta.next, &sm_chunk = cta.chunk;
     int (&sm_park)[3] = cta.park;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const ShardWindow sw = shard_window(a.wg_begin, dispatch_end(a), a.il_chunk, a.il_rank, a.il_n);
+    static_assert(PPC <= THREADS, "one request per thread");
     int nprobes;
     {
+        // the window from the host's bound first (no wait for the device-side count unless its start depends on it),
+        // the batch's requests fetched, and only then the real end
+        const bool early = window_needs_count(a);
+        ShardWindow sw = shard_window(a.wg_begin, early ? dispatch_end(a) : a.wg_end, a.il_chunk, a.il_rank, a.il_n);
         const long long wg0 = il_map(sw.first, a.il_chunk, a.il_rank, a.il_n, (long long)blockIdx.x * PPC);   // il_chunk % PPC == 0
-        const long long left = sw.end - wg0;
+        long long left = sw.end - wg0;
         if (left <= 0) return;                                   // uniform per CTA (end of the shard)
+        short4 rq = make_short4(0, 0, 0, 0);
+        if (tid < PPC && tid < left) rq = a.requests[(wg0 + tid) * (long long)a.size + a.shift];    // (inside max_requests even beyond the real count)
+        if (!early) { const long long e = dispatch_end(a); left = (e < sw.end ? e : sw.end) - wg0; if (left <= 0) return; }
         nprobes = left < PPC ? (int)left : PPC;
-        for (int i = tid; i < nprobes; i += THREADS) sm_req[i] = a.requests[(wg0 + i) * (long long)a.size + a.shift];
+        if (tid < nprobes) sm_req[tid] = rq;
         if (tid == 0) { sm_next = 0; sm_park[0] = 0; sm_park[1] = 0; sm_park[2] = 0; sm_chunk = 0; cta.wg0 = wg0; }
     }
     const int nrays = nprobes * R;
@@ -501,6 +522,19 @@ struct ExchangeWait {
     volatile unsigned *status;             // set to 1 when a rank never arrived
 };
 
+// flag reads of the exchange: acquire at system scope (what follows cannot be read before the flag)
+__device__ __forceinline__ unsigned load_acquire_sys(const volatile unsigned *p) {
+#ifdef __CUDA_ARCH__
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    const unsigned v = *p;
+    __threadfence_system();
+    return v;
+#endif
+}
+
 // Deferred imageStore (radiance.comp:353): scatter the staged texels of workgroups [wg_begin, wg_end) into the field
 // once every read of the old field is done.  In a multi-GPU frame the staged array is this rank's inbox: every rank
 // (this one included) stored the texels of its own workgroups there during its trace kernel, and xw names the epoch
@@ -515,11 +549,10 @@ __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__re
         if (threadIdx.x == 0) {
             const long long t0 = clock64();
             for (int p = 0; p < xw.n; p++)
-                while ((int)(xw.flags[p] - xw.epoch) < 0) {
+                while ((int)(load_acquire_sys(xw.flags + p) - xw.epoch) < 0) {
                     __nanosleep(100);
                     if (clock64() - t0 > xw.timeout_cycles) { *xw.status = 1u; break; }
                 }
-            __threadfence_system();
         }
         __syncthreads();
     }
@@ -531,6 +564,47 @@ __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__re
     if (rq.z < z_begin || rq.z >= z_end) return;
     if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz)
         field[rq.x + wx * (rq.y + wy * rq.z)] = __ldcv(staged + w);      // written by peers: not through a stale L1 line
+}
+
+// ---- the exchange as a PULL: all-gather and commit in one kernel ------------------------------------------------
+// lumcu_update_shard_exchange: every rank traces its shard into its OWN staged[] (nothing remote in the trace kernel:
+// fine-grained peer stores from its last phase cost the trace 2 % at 8 ranks), publishes its arrival, and then this
+// kernel -- behind the wait for all flags -- walks the whole dispatch: the texel of workgroup w is read from the
+// staged[] of the rank that owns w (over NVLink unless it is this rank; consecutive workgroups have one owner, so the
+// remote reads are full 128-byte lines) and stored into the local field.  A persistent grid: each CTA waits for the
+// flags once.
+struct ShardSources { PeerWords staged; int chunk, n; };
+__global__ void __launch_bounds__(256) gather_commit_kernel(uint32_t *__restrict__ field, ShardSources src,
+                                                            const short4 *__restrict__ requests, long long wg_begin, long long wg_end,
+                                                            int size, int shift, int wx, int wy, int wz,
+                                                            const unsigned long long *__restrict__ nreq_dev, ExchangeWait xw) {
+    __shared__ long long bound[MAX_PEERS + 1];
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int p = 0; p < xw.n; p++)
+            while ((int)(load_acquire_sys(xw.flags + p) - xw.epoch) < 0) {
+                __nanosleep(100);
+                if (clock64() - t0 > xw.timeout_cycles) { *xw.status = 1u; break; }
+            }
+    }
+    if (nreq_dev) { const long long n = device_workgroups(nreq_dev, size); wg_end = n < wg_end ? n : wg_end; }
+    if ((int)threadIdx.x <= src.n) {                               // where shard r of the contiguous split starts
+        const ShardWindow sw = shard_window(wg_begin, wg_end, 0, (int)threadIdx.x, src.n);
+        bound[threadIdx.x] = src.n > 1 ? sw.first : (threadIdx.x == 0 ? wg_begin : wg_end);
+    }
+    __syncthreads();
+    for (long long w = wg_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; w < wg_end; w += (long long)gridDim.x * blockDim.x) {
+        int r = 0;
+        if (src.chunk == 0) {
+            for (int k = 1; k < src.n; k++) r += w >= bound[k] ? 1 : 0;
+        } else {
+            r = (int)(((unsigned)(w - wg_begin) / (unsigned)src.chunk) % (unsigned)src.n);
+        }
+        const uint32_t word = __ldcv(src.staged.p[r] + w);
+        const short4 rq = requests[w * (long long)size + shift];
+        if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz)
+            field[rq.x + wx * (rq.y + wy * rq.z)] = word;
+    }
 }
 
 // "This rank has finished tracing epoch `epoch`, and everything it stored into the other ranks' inboxes is visible":

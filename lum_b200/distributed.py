@@ -8,9 +8,9 @@ their slabs -- either with ONE in-place all-gather (all_gather_field), or fused 
 lumcu_update_slab_exchange stores every new texel straight into all ranks' field replicas over NVLink
 peer memory between two flag barriers (open_peer_exchange wires it) -- after which every rank holds the
 identical new field for the next frame's gathers.  With the fused exchange a rank's texels need not be contiguous
-in the field, so the sharding there is by workgroup index (lumcu_update_shard_exchange): CONTIGUOUS equal ranges of
-the dispatch by default (equal probe counts whatever the scene looks like; each rank touches only its part of the
-world), or INTERLEAVED chunks of SHARD_CHUNK (lumcu_set_shard_mode), which also balance the cost per probe.  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
+in the field, so the sharding there is by workgroup index (lumcu_update_shard_exchange): INTERLEAVED chunks of
+SHARD_CHUNK workgroups by default (every rank samples every part of the world, so the ranks finish together whatever
+the scene looks like), or CONTIGUOUS equal ranges of the dispatch (lumcu_set_shard_mode).  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
 CPU for the tests of this host-side logic).
 """
 from __future__ import annotations
@@ -22,7 +22,7 @@ SHARD_CHUNK = 3072      # = IL_CHUNK of csrc/lumcu.cu: a multiple of every poole
 def shard_workgroups(nwg: int, rank: int, world_size: int, chunk: int = SHARD_CHUNK):
     """Workgroup indices of [0, nwg) that shard `rank` of `world_size` owns, in the order the kernels visit them
     (lumcu_update_shard).  chunk > 0 (LUMCU_SHARD_INTERLEAVED): chunk c of the dispatch belongs to rank
-    c % world_size.  chunk == 0 (LUMCU_SHARD_CONTIGUOUS, the stage's default): [nwg*rank/n, nwg*(rank+1)/n)."""
+    c % world_size (the stage's default).  chunk == 0 (LUMCU_SHARD_CONTIGUOUS): [nwg*rank/n, nwg*(rank+1)/n)."""
     import numpy as np
     w = np.arange(nwg, dtype=np.int64)
     if chunk == 0:

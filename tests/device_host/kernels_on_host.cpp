@@ -113,19 +113,23 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
     return 0;
 }
 
-// `frames` frames on `nranks` devices as lumcu_update_shard_exchange runs them: in epoch e every rank traces its
-// interleaved shard reading its own replica of the field, the new texels going into half e & 1 of EVERY rank's inbox
-// straight from the trace kernel; then arrive_kernel publishes e in every rank's flag array, and each rank's
-// commit_kernel -- which waits for all flags -- scatters the whole dispatch from its own inbox into its own replica.
-// (Ranks run one after another here, so every flag is already there when a commit looks; what is checked is the index
-// arithmetic, the parity halves and that every replica ends up equal to the single-device field.)
-// replicas: uint32 [nranks][cells], in = old field, out = field after the last frame.  il_chunk must be a multiple of
-// the pooled kernel's probes per CTA (lumcu.cu uses 3072; small here so that a small dispatch is really dealt out).
+// `frames` frames on `nranks` devices as the exchange runs them.  In epoch e every rank traces its shard reading its own
+// replica of the field; arrive_kernel publishes e in every rank's flag array; then
+//   push == 0 (lumcu_update_shard_exchange): the trace wrote half e & 1 of the rank's OWN staged[], and each rank's
+//             gather_commit_kernel -- which waits for all flags -- reads every workgroup's texel from its owner's staged[]
+//             and stores it into its own replica;
+//   push == 1 (lumcu_update_slab_exchange's transfer): the trace stored the new texels into half e & 1 of EVERY rank's
+//             inbox from its last phase, and each rank's commit_kernel scatters the whole dispatch from its own inbox.
+// (Ranks run one after another here, so every flag is already there when a kernel looks; what is checked is the index
+// arithmetic -- shard windows, owners, parity halves -- and that every replica ends up equal to the single-device field.)
+// replicas: uint32 [nranks][cells], in = old field, out = field after the last frame.  il_chunk: 0 = contiguous shards,
+// else a multiple of the pooled kernel's probes per CTA (lumcu.cu uses 3072; small here so that a small dispatch is
+// really dealt out).
 extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capacity, int brick0_empty, int R, float reactiveness,
                                               const int16_t *world, const uint8_t *bricks, const float *materials,
                                               uint32_t *replicas, int nranks, int il_chunk,
                                               const int16_t *requests, long long nreq, int time_seed, int size, int shift,
-                                              const float *table, const float *sun3, int variant, int frames) {
+                                              const float *table, const float *sun3, int variant, int frames, int push) {
     if (nranks < 1 || nranks > MAX_PEERS) return -1;
     const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? nreq / size : 0;
     const size_t half = (size_t)std::max<long long>(nwg_all, 1);
@@ -143,7 +147,7 @@ extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capaci
             const long long traced = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials,
                                                    replicas + (size_t)r * cells, requests, nreq, time_seed + f, size, shift, table, sun3,
                                                    variant, Interleave{il_chunk, r, nranks}, staged[r].data() + parity * half,
-                                                   nullptr, nullptr, nullptr, tot, &inbox);
+                                                   nullptr, nullptr, nullptr, tot, push ? &inbox : nullptr);
             if (traced < 0) return -1;
             PeerFlags pf{};
             pf.n = nranks; pf.rank = r;
@@ -151,13 +155,20 @@ extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capaci
             emu_launch(1, 1, 32, [&] { arrive_kernel(pf, epoch); });
         }
         const int ct = 64;
-        for (int r = 0; r < nranks; r++)
-            if (nwg_all > 0)
+        for (int r = 0; r < nranks; r++) {
+            if (nwg_all <= 0) continue;
+            const ExchangeWait xw{flags[r].data(), nranks, epoch, 1ll << 40, &status};
+            if (push)
                 emu_launch((unsigned)((nwg_all + ct - 1) / ct), 1, ct, [&] {
                     commit_kernel(replicas + (size_t)r * cells, staged[r].data() + parity * half, reinterpret_cast<const short4 *>(requests),
-                                  0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, Interleave{il_chunk, 0, 1}, nullptr,
-                                  ExchangeWait{flags[r].data(), nranks, epoch, 1ll << 40, &status});
+                                  0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, Interleave{il_chunk, 0, 1}, nullptr, xw);
                 });
+            else
+                emu_launch(3, 1, ct, [&] {                          // a persistent grid: 3 CTAs stride over the dispatch
+                    gather_commit_kernel(replicas + (size_t)r * cells, ShardSources{inbox, il_chunk, nranks},
+                                         reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz, nullptr, xw);
+                });
+        }
     }
     return status ? -2 : 0;
 }

@@ -253,12 +253,14 @@ def test_slab_bound_kernel(emu, oracle_mod, demo):
             assert (int(out[0]), int(out[1])) == (int(np.searchsorted(zs, zb, "left")), int(np.searchsorted(zs, ze, "left")))
 
 
+@pytest.mark.parametrize("push", [0, 1], ids=["pull", "push"])
 @pytest.mark.parametrize("chunk", [12, 0], ids=["interleaved", "contiguous"])
 @pytest.mark.parametrize("nranks,variant", [(2, POOL), (3, POOL), (2, WG)])
-def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant, chunk):
-    """SURVEY 8e on the emulator: three frames dealt to `nranks` ranks in interleaved chunks (il_map in the kernels), every
-    rank's texels stored into every rank's inbox from the trace kernel (alternating halves), arrive_kernel, then each rank's
-    commit_kernel behind the flag wait -- all replicas equal the single-device field after every frame."""
+def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant, chunk, push):
+    """SURVEY 8e on the emulator: three frames dealt to `nranks` ranks (contiguous shards or interleaved chunks, il_map /
+    shard_window in the kernels), arrive_kernel, then the transfer -- pull: gather_commit_kernel reads every texel from its
+    owner's staged[] (alternating halves); push: the trace stored into every rank's inbox and commit_kernel scatters locally
+    -- behind the flag wait: all replicas equal the single-device field."""
     O = oracle_mod
     sc = scene_of(O, small_synth)
     req = np.ascontiguousarray(O.build_requests(small_synth["world"])[::53][:45], np.int16)      # 45 probes, chunks of 12
@@ -278,7 +280,7 @@ def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nrank
     rc = emu.kernels_on_host_update_sharded(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]), C.c_int(1),
                                             C.c_int(64), C.c_float(0.01), p(world), p(bricks), p(mats), p(replicas),
                                             C.c_int(nranks), C.c_int(chunk), p(req), C.c_longlong(len(req)), C.c_int(4),
-                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant), C.c_int(3))
+                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant), C.c_int(3), C.c_int(push))
     assert rc == 0
     for r in range(nranks):
         assert np.array_equal(replicas[r], ref), r

@@ -39,6 +39,32 @@ timed("update (validated world)", lambda k: st.update(k))
 def up_update(k):
     st.upload_world_async(r.world_host); st.build_requests(sync=False); st.update(k)
 timed("upload + build + update", up_update)
+def seq(*parts):
+    def f(k):
+        for q in parts:
+            q(k)
+    return f
+U = lambda k: st.upload_world_async(r.world_host)
+B0 = lambda k: st.build_requests(sync=False)
+B1 = lambda k: st.build_requests()
+X = lambda k: st.update(k)
+timed("build(async) + update", seq(B0, X))
+timed("build(sync) + update", seq(B1, X))
+timed("upload + update", seq(U, X))
+timed("upload + build(sync) + update", seq(U, B1, X))
+st.set_profiling(True)
+for name, fn in (("update alone", X), ("upload + build(async) + update", seq(U, B0, X)), ("upload + update", seq(U, X)), ("build(async) + update", seq(B0, X))):
+    ks = []
+    for k in range(6):
+        r.flush_l2(k); fn(k); st.wait_idle(); ks.append(st.last_kernel_ms())
+    print(f"trace kernel alone inside '{name}': {np.mean(ks[2:]):.3f} ms")
+for flips in range(3):
+    ks = []
+    for k in range(6):
+        r.flush_l2(k); X(k); st.wait_idle(); ks.append(st.last_kernel_ms())
+    print(f"trace kernel, update alone, after {flips} more world-buffer flips: {np.mean(ks[2:]):.3f} ms")
+    U(0); st.wait_idle()
+st.set_profiling(False)
 timed("download_field_async + fence wait", lambda k: (st.download_field_async(r.field_host2[0]), st.record_fence(0), st.wait_fence(0)))
 for span in (False, True):
     tot, per = r.timed(r.step_e2e, steps, 3, span=span)
