@@ -541,7 +541,7 @@ def cpu_baseline(scene, budget_s, threads=0, rays=RAYS):
     dt = time.perf_counter() - t0
     return dict(value=len(sample) * rays / dt, unit=UNIT, cores=int(r["threads"]), kind="port",
                 sample=f"{len(sample)} of {len(req)} probes (every {max(1, len(req) // n)}-th request, "
-                       f"time_seed 1, zero field), {dt:.2f} s wall, OpenMP over probes"), sample, sc, f0
+                       f"time_seed 1, zero field), {dt:.2f} s wall, OpenMP over probes"), sample, sc, f0, len(req)
 
 
 def run_reference(args, rank):
@@ -554,7 +554,7 @@ def run_reference(args, rank):
     scene = make_scene(args.workload)
     nsteps = args.steps + args.warmup
     budget = max(1.0, min(20.0, 150.0 / max(1, nsteps)))
-    base, sample, sc, f0 = cpu_baseline(scene, budget, rays=args.rays_per_probe)
+    base, sample, sc, f0, nprobes = cpu_baseline(scene, budget, rays=args.rays_per_probe)
     RAYS = args.rays_per_probe
     for i in range(args.warmup):
         O.update(sc, f0, sample, i, nthreads=host_threads())
@@ -566,8 +566,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "rays_per_probe": RAYS,
-                                            "sample_probes": int(len(sample))},
+            "data": "synthetic", "config": workload_config(args, max(1, args.gpus), nprobes, RAYS),
+            "sample_probes": int(len(sample)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": base["cores"], "kind": "port",
                              "sample": base["sample"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -587,6 +587,20 @@ def run_reference(args, rank):
     except Exception as e:
         line["reference_shader_on_cpu"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world_size, probes, rays):
+    """The `config` object of the JSON line -- the same for both arms (the reference arm times a bounded SAMPLE of
+    this workload, described in its cpu_baseline.sample; the per-ray metric is what makes the two comparable)."""
+    fused = args.exchange == "fused"
+    par = "single GPU"
+    if world_size > 1:
+        par = f"probes sharded x{world_size}: " + (
+            ("contiguous equal ranges of the dispatch" if args.shard_mode == "contiguous" else "interleaved chunks of 3072 workgroups")
+            + "; one flag barrier per frame, then one kernel reads every texel from its owner's staging array over NVLink and commits it locally"
+            if fused else "z-slabs + NCCL field all-gather")
+    return {"workload": args.workload, "probes": int(probes), "rays_per_probe": int(rays), "rays_per_step": int(probes) * int(rays),
+            "parallelism": par, "l2": "flushed between timed steps (256 MiB fill)", "time_seed": "step index", "initial_field": "zero"}
 
 
 KERNEL_NAMES = {True: "lumcu::radiance_update_pool_kernel<{r}, {t}, 3, false>", False: "lumcu::radiance_update_wg_kernel<{r}, false>"}
@@ -672,11 +686,7 @@ def run_ours(args, rank, local_rank, world_size):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": args.workload, "probes": m["probes"], "rays_per_probe": rays,
-                           "rays_per_step": m["rays"], "parallelism": (f"probes sharded x{world_size}: " + (("contiguous equal ranges of the dispatch" if args.shard_mode == "contiguous" else "interleaved chunks of 3072 workgroups") + "; one flag barrier per frame, then one kernel reads every texel from its owner's staging array over NVLink and commits it locally"
-                                                                             if runner.fused else "z-slabs + NCCL field all-gather"))
-                           if world_size > 1 else "single GPU", "l2": "flushed between timed steps (256 MiB fill)",
-                           "time_seed": "step index", "initial_field": "zero"},
+                "config": workload_config(args, world_size, m["probes"], rays),
                 "e2e": {"value": m["e2e_value"], "unit": UNIT, "ms_per_step": m["e2e_ms"],
                         "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
                         "frames_in_flight": 2, "stream_ms_upload_build_update_download": m["e2e_phases"]},

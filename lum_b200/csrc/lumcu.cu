@@ -101,7 +101,17 @@ struct LumcuCtx {
     float4 *d_mat4 = nullptr;              // {r,g,b,emmit} per id, repacked at upload (the shading phase's one load)
     uint32_t *d_field = nullptr;
     uint32_t *d_field_tmp = nullptr;       // shift scratch (lazy)
-    short4 *d_requests = nullptr;
+    short4 *d_requests = nullptr;          // = d_requests_buf[req_cur]: the list the next launches read
+    short4 *d_requests_buf[2] = {nullptr, nullptr};     // two lists: a list built ahead goes into the other one while the
+    unsigned long long *d_total_buf[2] = {nullptr, nullptr};   // frame in flight still reads this one (with its own count)
+    int req_cur = 0;
+    cudaEvent_t ev_list_retired[2] = {nullptr, nullptr};       // "everything queued before the flip away from list b has run"
+    bool list_retired[2] = {false, false};
+    cudaStream_t prep_stream = nullptr;    // high priority: next frame's request build + world validation, beside this frame's trace
+    cudaEvent_t ev_prep = nullptr, ev_world_ready = nullptr, ev_scratch = nullptr;
+    bool world_ready_pending = false;      // ev_world_ready marks an upload the prep stream has not waited for yet
+    bool scratch_on_stream = false;        // the builder's scratch was last used on `stream` (ev_scratch), not on prep_stream
+
     uint32_t *d_staged = nullptr;
     float *d_table = nullptr;
     std::vector<float> h_table;
@@ -118,7 +128,7 @@ struct LumcuCtx {
     int shard_chunk = IL_CHUNK;  // lumcu_set_shard_mode: IL_CHUNK = interleaved chunks (default), 0 = contiguous shards
     int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
     bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
-    uint32_t *d_scene_flags = nullptr;     // bit 0: world ids outside the palette (validate_world_kernel)
+    uint32_t *d_scene_flags = nullptr;     // [2], one word per world buffer; bit 0: world ids outside the palette (validate_world_kernel)
     bool world_dirty = true;     // the world changed since the last validation
     bool world_shared = false;   // its device address was handed out: validate before every update
 
@@ -263,14 +273,20 @@ int ensure_debug(LumcuCtx *c) {
 }
 
 // Device-side check that every world id is inside the palette (what march_step_fast relies on); no host sync.
+// One flag word per world buffer, so that the check of the next frame's world can run while this frame still traces.
+int launch_validate(LumcuCtx *c, cudaStream_t st) {
+    uint32_t *flag = c->d_scene_flags + c->world_cur;
+    CU(cudaMemsetAsync(flag, 0, sizeof(uint32_t), st));
+    const int vt = 256;
+    const long long vb = std::min<long long>((c->cells + vt - 1) / vt, (long long)c->sm_count * 8);
+    validate_world_kernel<<<(unsigned)vb, vt, 0, st>>>(c->d_world, c->cells, c->desc.palette_capacity, flag);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
 int ensure_validated(LumcuCtx *c) {
     if (c->world_dirty || c->world_shared) {
-        CU(cudaMemsetAsync(c->d_scene_flags, 0, sizeof(uint32_t), c->stream));
-        const int vt = 256;
-        const long long vb = std::min<long long>((c->cells + vt - 1) / vt, (long long)c->sm_count * 8);
-        validate_world_kernel<<<(unsigned)vb, vt, 0, c->stream>>>(c->d_world, c->cells, c->desc.palette_capacity, c->d_scene_flags);
-        c->launches++;
-        CU(cudaGetLastError());
+        if (int rc = launch_validate(c, c->stream)) return rc;
         c->world_dirty = false;
     }
     return 0;
@@ -278,7 +294,7 @@ int ensure_validated(LumcuCtx *c) {
 
 SceneView scene_view(LumcuCtx *c) {
     return SceneView{c->d_world, c->d_bricks, c->d_materials, c->d_mat4, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
-                     c->brick0_empty ? 1 : 0, c->d_scene_flags
+                     c->brick0_empty ? 1 : 0, c->d_scene_flags + c->world_cur
     };
 }
 
@@ -460,12 +476,24 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     CUB(cudaEventCreate(&c->ev_k1));
     CUB(cudaMalloc(&c->d_world_buf[0], (size_t)c->cells * sizeof(int16_t)));
     c->d_world = c->d_world_buf[0];        // (the second buffer is allocated by the first lumcu_upload_world_async)
-    CUB(cudaMalloc(&c->d_scene_flags, sizeof(uint32_t)));
+    CUB(cudaMalloc(&c->d_scene_flags, 2 * sizeof(uint32_t)));
+    CUB(cudaMemsetAsync(c->d_scene_flags, 0, 2 * sizeof(uint32_t), c->stream));
+    {
+        int lo = 0, hi = 0;
+        CUB(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUB(cudaStreamCreateWithPriority(&c->prep_stream, cudaStreamNonBlocking, hi));
+    }
+    CUB(cudaEventCreateWithFlags(&c->ev_prep, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_world_ready, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_list_retired[0], cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_list_retired[1], cudaEventDisableTiming));
     CUB(cudaMalloc(&c->d_bricks, (size_t)d->palette_capacity * 4096));
     CUB(cudaMalloc(&c->d_materials, 256 * 6 * sizeof(float)));
     CUB(cudaMalloc(&c->d_mat4, 256 * sizeof(float4)));
     CUB(cudaMalloc(&c->d_field, (size_t)c->cells * sizeof(uint32_t)));
-    CUB(cudaMalloc(&c->d_requests, (size_t)c->max_requests * sizeof(short4)));
+    CUB(cudaMalloc(&c->d_requests_buf[0], (size_t)c->max_requests * sizeof(short4)));
+    c->d_requests = c->d_requests_buf[0];  // (the second list and the builder's scratch are allocated on first use)
     CUB(cudaMalloc(&c->d_staged, 2 * (size_t)c->max_requests * sizeof(uint32_t)));   // two halves: the exchange alternates
     CUB(cudaMalloc(&c->d_table, (size_t)R * 3 * sizeof(float)));
     CUB(cudaMemsetAsync(c->d_world, 0, (size_t)c->cells * sizeof(int16_t), c->stream));
@@ -496,11 +524,12 @@ int lumcu_destroy(LumcuCtx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->dl_stream) cudaStreamSynchronize(c->dl_stream);
+    if (c->prep_stream) cudaStreamSynchronize(c->prep_stream);
     cudaFree(c->d_scene_flags);
     cudaFree(c->d_g_matnorm); cudaFree(c->d_g_depth); cudaFree(c->d_g_frame); cudaFree(c->d_g_cov);
     cudaFree(c->d_world_buf[0]); cudaFree(c->d_world_buf[1]); cudaFree(c->d_bricks); cudaFree(c->d_materials); cudaFree(c->d_mat4); cudaFree(c->d_field);
-    cudaFree(c->d_field_tmp); cudaFree(c->d_requests); cudaFree(c->d_staged); cudaFree(c->d_table);
-    cudaFree(c->d_flags); cudaFree(c->d_tile_state); cudaFree(c->d_total);
+    cudaFree(c->d_field_tmp); cudaFree(c->d_requests_buf[0]); cudaFree(c->d_requests_buf[1]); cudaFree(c->d_staged); cudaFree(c->d_table);
+    cudaFree(c->d_flags); cudaFree(c->d_tile_state); cudaFree(c->d_total_buf[0]); cudaFree(c->d_total_buf[1]);
     lumcu_peers_close(c);
     cudaFree(c->d_sync_flags);
     if (c->h_status) cudaFreeHost(c->h_status);
@@ -518,6 +547,8 @@ int lumcu_destroy(LumcuCtx *c) {
     if (c->ev_dl_ready) cudaEventDestroy(c->ev_dl_ready);
     if (c->ev_dl_done) cudaEventDestroy(c->ev_dl_done);
     for (auto &e : c->ev_world_retired) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev_prep, c->ev_world_ready, c->ev_scratch, c->ev_list_retired[0], c->ev_list_retired[1]}) if (e) cudaEventDestroy(e);
+    if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
     if (c->dl_stream) cudaStreamDestroy(c->dl_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -553,6 +584,8 @@ int lumcu_upload_world(LumcuCtx *c, const int16_t *world) {
     if (int rc = use(c)) return rc;
     if (!world) return fail(LUMCU_E_ARG, "null world");
     if (int rc = staged_upload(c, c->stage_world, c->d_world, world, (size_t)c->cells * sizeof(int16_t))) return rc;
+    CU(cudaEventRecord(c->ev_world_ready, c->stream));
+    c->world_ready_pending = true;
     c->have_world = true;
     c->world_dirty = true;
     return 0;
@@ -577,6 +610,8 @@ int lumcu_upload_world_async(LumcuCtx *c, const int16_t *world) {
     if (c->world_retired[nxt]) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_world_retired[nxt], 0));
     CU(cudaMemcpyAsync(c->d_world_buf[nxt], world, bytes, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_copy, c->copy_stream));
+    CU(cudaEventRecord(c->ev_world_ready, c->copy_stream));
+    c->world_ready_pending = true;
     CU(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     c->world_cur = nxt;
     c->d_world = c->d_world_buf[nxt];
@@ -748,25 +783,54 @@ int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, 
     if (!c->d_flags) {
         CU(cudaMalloc(&c->d_flags, (size_t)c->cells));
         CU(cudaMalloc(&c->d_tile_state, ((size_t)ntiles + 1) * sizeof(unsigned long long)));     // [ntiles] = the ticket counter
-        CU(cudaMalloc(&c->d_total, 2 * sizeof(unsigned long long)));
     }
-    CU(cudaMemsetAsync(c->d_tile_state, 0, ((size_t)ntiles + 1) * sizeof(unsigned long long), c->stream));
-    build_fused_kernel<<<(unsigned)ntiles, BUILD_THREADS, 0, c->stream>>>(c->d_world, c->wx, c->wy, c->wz, c->d_flags, c->d_tile_state,
-                                                                        (unsigned int *)(c->d_tile_state + ntiles), c->d_requests,
-                                                                        c->max_requests, c->d_total);
+    // A list nobody waits for (no count wanted, no specials to upload first) is built AHEAD: into the other list buffer,
+    // on the high-priority prep stream, as soon as the world it is built from has arrived -- beside the trace of the
+    // frame in flight, which still reads the current list -- together with that world's validation.  The stage's
+    // stream waits for it here, so everything queued from now on sees the new list.  Otherwise: in place, in order.
+    const bool ahead = !out_count && nspecial == 0;
+    const int tgt = ahead ? c->req_cur ^ 1 : c->req_cur;
+    if (!c->d_requests_buf[tgt]) CU(cudaMalloc(&c->d_requests_buf[tgt], (size_t)c->max_requests * sizeof(short4)));
+    if (!c->d_total_buf[tgt]) CU(cudaMalloc(&c->d_total_buf[tgt], 2 * sizeof(unsigned long long)));
+    cudaStream_t st = ahead ? c->prep_stream : c->stream;
+    if (ahead) {
+        CU(cudaEventRecord(c->ev_list_retired[c->req_cur], c->stream));        // every reader of the current list has been queued by now
+        c->list_retired[c->req_cur] = true;
+        if (c->list_retired[tgt]) CU(cudaStreamWaitEvent(st, c->ev_list_retired[tgt], 0));
+        if (c->world_ready_pending) { CU(cudaStreamWaitEvent(st, c->ev_world_ready, 0)); c->world_ready_pending = false; }
+        if (c->scratch_on_stream) { CU(cudaStreamWaitEvent(st, c->ev_scratch, 0)); c->scratch_on_stream = false; }
+        if (c->world_dirty && !c->world_shared) {
+            if (int rc = launch_validate(c, st)) return rc;
+            c->world_dirty = false;
+        }
+    }
+    CU(cudaMemsetAsync(c->d_tile_state, 0, ((size_t)ntiles + 1) * sizeof(unsigned long long), st));
+    build_fused_kernel<<<(unsigned)ntiles, BUILD_THREADS, 0, st>>>(c->d_world, c->wx, c->wy, c->wz, c->d_flags, c->d_tile_state,
+                                                                  (unsigned int *)(c->d_tile_state + ntiles), c->d_requests_buf[tgt],
+                                                                  c->max_requests, c->d_total_buf[tgt]);
     c->launches++;
     CU(cudaGetLastError());
-    if (nspecial > 0) {
-        if (c->special_cap < nspecial) {
-            cudaFree(c->d_special); c->d_special = nullptr; c->special_cap = 0;
-            CU(cudaMalloc(&c->d_special, (size_t)nspecial * sizeof(short4)));
-            c->special_cap = nspecial;
+    if (ahead) {
+        CU(cudaEventRecord(c->ev_prep, st));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_prep, 0));
+        c->req_cur = tgt;
+    } else {
+        if (nspecial > 0) {
+            if (c->special_cap < nspecial) {
+                cudaFree(c->d_special); c->d_special = nullptr; c->special_cap = 0;
+                CU(cudaMalloc(&c->d_special, (size_t)nspecial * sizeof(short4)));
+                c->special_cap = nspecial;
+            }
+            if (int rc = staged_upload(c, c->stage_misc, c->d_special, special, (size_t)nspecial * sizeof(short4))) return rc;
+            build_specials_kernel<<<1, 1024, 0, c->stream>>>(c->d_flags, c->wx, c->wy, c->wz, c->d_special, nspecial, c->d_requests_buf[tgt], c->d_total_buf[tgt], c->max_requests);
+            c->launches++;
+            CU(cudaGetLastError());
         }
-        if (int rc = staged_upload(c, c->stage_misc, c->d_special, special, (size_t)nspecial * sizeof(short4))) return rc;
-        build_specials_kernel<<<1, 1024, 0, c->stream>>>(c->d_flags, c->wx, c->wy, c->wz, c->d_special, nspecial, c->d_requests, c->d_total, c->max_requests);
-        c->launches++;
-        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev_scratch, c->stream));
+        c->scratch_on_stream = true;
     }
+    c->d_requests = c->d_requests_buf[tgt];
+    c->d_total = c->d_total_buf[tgt];
     // The count stays on the device: the kernels of the frame cut their dispatch down to it, and nothing here waits
     // for the GPU.  Until somebody asks (out_count, lumcu_request_count, ...) the host works with an upper bound.
     c->count_on_device = true;
@@ -1128,6 +1192,7 @@ int lumcu_debug_unpack_table(LumcuCtx *c, float *out) {
 
 int lumcu_wait_idle(LumcuCtx *c) {
     if (int rc = use(c)) return rc;
+    CU(cudaStreamSynchronize(c->prep_stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->dl_stream));
     CU(cudaStreamSynchronize(c->copy_stream));

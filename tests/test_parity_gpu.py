@@ -497,29 +497,41 @@ def test_slab_update_is_jacobi_across_its_two_passes(oracle_mod, demo):
     st.close()
 
 
+@pytest.mark.parametrize("with_specials", [False, True], ids=["ahead", "in-place"])
 @pytest.mark.parametrize("variant", [0, 1])
-def test_async_build_and_device_side_count(oracle_mod, demo, variant):
+def test_async_build_and_device_side_count(oracle_mod, demo, variant, with_specials):
     """lumcu_build_requests(out_count = NULL): nothing waits for the GPU, the launches are sized for an upper bound of
     the request count (14x the real one on the demo world) and the kernels stop at the count they read on the device.
-    Two frames queued back to back, world uploaded from pinned memory without a wait, result read back through the
-    asynchronous download + fence: equal to the synchronous path and to the oracle."""
+    Without specials the list is built AHEAD -- other list buffer, prep stream, beside the frame in flight, with the
+    world's validation -- so the frames here alternate between two different worlds (uploaded from pinned memory
+    without a wait, into alternating world buffers): a stale list, count, world or validation flag would show.  Five
+    frames queued back to back, result read back through the asynchronous download + fence: equal to the oracle."""
     import torch
     O = oracle_mod
-    sc = oracle_scene(O, demo)
-    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0)], np.int16)
-    req = O.build_requests(demo["world"], sp)
-    f0 = np.random.default_rng(5).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
-    ref = f0
-    for f in range(2):
+    w0 = np.ascontiguousarray(demo["world"], np.int16)
+    w1 = w0.copy()
+    w1[8:, :, :] = 0                      # the upper half cleared ...
+    w1[9, 20:30, 20:30] = 3               # ... and a floating slab of stone: other requests, other count
+    worlds = [w0, w1]
+    sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0)], np.int16) if with_specials else None
+    f0 = np.random.default_rng(5).integers(0, 2 ** 32, w0.size, dtype=np.uint64).astype(np.uint32)
+    ref, counts = f0, []
+    for f in range(5):
+        w = worlds[f & 1]
+        sc = O.Scene(w, demo["bricks"], demo["materials"])
+        req = O.build_requests(w, sp)
+        counts.append(len(req))
         ref = O.update(sc, ref, req, 40 + f)["field"]
+    assert counts[0] != counts[1]
     st = make_stage(demo)
     st.set_kernel_variant(variant)
-    pin_w = torch.empty(sc.cells, dtype=torch.int16, pin_memory=True)
-    pin_f = torch.empty(sc.cells, dtype=torch.int32, pin_memory=True)
-    pin_w.numpy()[:] = np.ascontiguousarray(demo["world"], np.int16).reshape(-1)
+    pins = [torch.empty(w0.size, dtype=torch.int16, pin_memory=True) for _ in range(2)]
+    for p, w in zip(pins, worlds):
+        p.numpy()[:] = w.reshape(-1)
+    pin_f = torch.empty(w0.size, dtype=torch.int32, pin_memory=True)
     st.upload_field(f0)
-    for f in range(2):
-        st.upload_world_async(pin_w.numpy())
+    for f in range(5):
+        st.upload_world_async(pins[f & 1].numpy())
         assert st.build_requests(sp, sync=False) is None
         st.update(40 + f)
     out = pin_f.numpy().view(np.uint32)
@@ -527,11 +539,19 @@ def test_async_build_and_device_side_count(oracle_mod, demo, variant):
     st.record_fence(1)
     st.wait_fence(1)
     assert np.array_equal(out, ref)
-    assert st.request_count() == len(req)                      # the host learns the count when it asks
-    assert np.array_equal(st.download_requests(), req)
+    assert st.request_count() == counts[4]                     # the host learns the count when it asks
+    assert np.array_equal(st.download_requests(), O.build_requests(worlds[0], sp))
+    # a synchronous build after builds ahead (shares the builder's scratch), then ahead again
+    assert st.build_requests(sp) == counts[0]
+    st.upload_world_async(pins[1].numpy())
+    st.build_requests(sync=False)
+    st.update(99)
+    sc1 = O.Scene(w1, demo["bricks"], demo["materials"])
+    ref = O.update(sc1, ref, O.build_requests(w1), 99)["field"]
+    assert np.array_equal(st.download_field(), ref)
     st.wait_fence(3)                                           # never recorded: returns at once
     st.close()
-    del pin_w, pin_f
+    del pins, pin_f
 
 
 def test_brick_copy_list_must_not_alias(demo):
