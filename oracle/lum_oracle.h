@@ -19,8 +19,11 @@
  * What stays a DECREE (DESIGN.md "Oracle semantics"), because a Vulkan driver and not the
  * shader text defines it: the filter arithmetic of textureLod, the order of subgroupAdd,
  * out-of-range fetches, FMA contraction, the precision of normalize/sqrt/division, Jacobi
- * field update.  The shim and this file follow the same decrees.  Host-side C++ of the
- * reference (request list, blockify) is restated only: PARITY UNPINNED for those functions.
+ * field update.  The shim and this file follow the same decrees.  The host-side C++ of the
+ * reference on the path (request-list rule, get_shift, blockify_mesh, map_mesh's arithmetic) is
+ * pinned the same way: cut out of internal_render.cpp verbatim and compiled in place
+ * (oracle/host_prep.py, oracle/ref_host.cpp -> oracle/_ref/libref_host.so), live and through
+ * tests/golden/ref_host_golden.npz (tests/test_ref_host.py): equal, floats bit for bit.
  *
  * All file:line citations are relative to the reference tree (/root/reference).
  */
