@@ -231,9 +231,9 @@ int lumcu_wait_idle(LumcuCtx *ctx);
 /* GPU time of the last update, the pair of timestamps around vkCmdDispatch
  * (internal_render.cpp:1205-1207, :2173 timeTakenByRadiance). */
 int lumcu_last_update_ms(LumcuCtx *ctx, float *ms);
-/* Kernel selection.  0 = one CTA per workgroup, the dispatch shape of radiance.comp itself (best
- * for demo-sized dispatches, which are latency-bound); 1 = pooled kernel, one CTA per 1024 rays
- * with lane-level ray refill (best once the GPU is full); 2 (default) = choose by dispatch size.
+/* Kernel selection.  0 = one CTA per workgroup, the dispatch shape of radiance.comp itself (best for demo-sized
+ * dispatches, which are latency-bound); 1 = pooled kernel, one CTA per 384 rays with lane-level ray refill (best once
+ * the dispatch gives it a wave of CTAs); 2 (default) = choose by dispatch size (pooled from 8,192 workgroups on).
  * All give bit-identical results. */
 int lumcu_set_kernel_variant(LumcuCtx *ctx, int32_t variant);
 

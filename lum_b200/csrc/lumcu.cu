@@ -119,6 +119,10 @@ struct LumcuCtx {
 
     long long nreq = 0;          // current request count -- an upper bound while count_on_device
     long long nsorted = 0;       // leading requests known to be z-sorted
+    long long count_hint = -1;      // the last request count the host has seen (a hint for kernel choice while count_on_device)
+    unsigned long long *h_count = nullptr;   // pinned: every build without a sync also queues a 16-byte copy of its count here
+    cudaEvent_t ev_count = nullptr;
+    bool count_copy_pending = false;
     bool count_on_device = false;   // the list was built without a host sync: the true count is *d_total (+ d_nbuilt),
                                     // the kernels cut their dispatch down to it, and the host learns it when asked
     bool have_world = false, have_bricks = false, have_materials = false;
@@ -309,6 +313,14 @@ long long il_count(long long total, const Interleave &il) {
 // The request count as the host needs it for launch sizes: exact, or (count_on_device) an upper bound.
 const unsigned long long *count_ptr(const LumcuCtx *c) { return c->count_on_device ? c->d_total : nullptr; }
 
+// Has the count of an earlier sync-less build arrived in pinned memory?  Never waits.
+void poll_count(LumcuCtx *c) {
+    if (c->count_copy_pending && cudaEventQuery(c->ev_count) == cudaSuccess) {
+        c->count_hint = (long long)c->h_count[0];
+        c->count_copy_pending = false;
+    }
+}
+
 // Learn the device-side count (one 16-byte readback + sync); every entry point that needs exact numbers calls this.
 int resolve_count(LumcuCtx *c) {
     if (!c->count_on_device) return 0;
@@ -322,6 +334,7 @@ int resolve_count(LumcuCtx *c) {
     }
     c->nreq = (long long)t[0];
     c->nsorted = (long long)t[1];
+    c->count_hint = c->nreq;
     return 0;
 }
 
@@ -383,7 +396,17 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         // the z filter (unsorted special tail of a slab update) only exists in the per-workgroup kernel
         // and small dispatches (demo-sized worlds) are latency-bound: they want one workgroup per CTA
         const bool unfiltered = z_begin <= -32768 && z_end >= 32768;
-        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && nwg * c->R >= (1ll << 23)));
+        // Which kernel (variant 2 = choose): the pooled kernel once the dispatch gives it about a wave of CTAs, i.e. from
+        // ~8 K workgroups on (B200, tools/kernel_crossover.py: 16 K probes -- pooled 0.048 / 0.098 / 0.31 ms against
+        // 0.064 / 0.115 / 0.36 at 16 / 64 / 256 rays per probe; the demo world's 2,689 probes -- 0.043 / 0.047 / 0.072
+        // against 0.028 / 0.033 / 0.062).  While the real count is still on the device the last count the host has
+        // seen stands in for it (poll_count); the launch itself stays sized for the bound.
+        long long est = nwg;
+        if (c->count_on_device) {
+            poll_count(c);
+            if (c->count_hint >= 0) est = std::min(nwg, il_count(c->count_hint / size, il));
+        }
+        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && est >= 8192));
         if (c->debug_flags) {
             if (c->count_on_device) return fail(LUMCU_E_STATE, "instrumented update with an unresolved request count");
             if (int rc = ensure_debug(c)) return rc;
@@ -537,6 +560,8 @@ int lumcu_destroy(LumcuCtx *c) {
     for (auto &m : c->models) cudaFree(m.d_vox);
     cudaFree(c->d_pre_blend); cudaFree(c->d_ray_samples); cudaFree(c->d_ray_hits); cudaFree(c->d_totals);
     c->stage_world.release(); c->stage_req.release(); c->stage_misc.release(); c->stage_pairs.release();
+    if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->ev_count) cudaEventDestroy(c->ev_count);
     for (auto &f : c->fences) if (f) cudaEventDestroy(f);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -770,6 +795,7 @@ int lumcu_set_requests(LumcuCtx *c, const int16_t *xyzw, int64_t n) {
         c->nsorted = 0;
     }
     c->nreq = n;
+    c->count_hint = n;
     c->count_on_device = false;
     c->req_version++;
     return 0;
@@ -831,6 +857,13 @@ int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, 
     }
     c->d_requests = c->d_requests_buf[tgt];
     c->d_total = c->d_total_buf[tgt];
+    {   // the count follows the host at its own pace: a 16-byte copy into pinned memory that the next frames poll
+        if (!c->h_count) { CU(cudaHostAlloc(&c->h_count, 2 * sizeof(unsigned long long), cudaHostAllocDefault)); CU(cudaEventCreateWithFlags(&c->ev_count, cudaEventDisableTiming)); }
+        poll_count(c);                                               // (do not lose an earlier count that has arrived)
+        CU(cudaMemcpyAsync(c->h_count, c->d_total, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ahead ? c->prep_stream : c->stream));
+        CU(cudaEventRecord(c->ev_count, ahead ? c->prep_stream : c->stream));
+        c->count_copy_pending = true;
+    }
     // The count stays on the device: the kernels of the frame cut their dispatch down to it, and nothing here waits
     // for the GPU.  Until somebody asks (out_count, lumcu_request_count, ...) the host works with an upper bound.
     c->count_on_device = true;
