@@ -142,7 +142,8 @@ int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, i
                                int32_t z_begin, int32_t z_end);
 /* Probe sharding by workgroup index (no z-sorted list needed).  lumcu_set_shard_mode chooses how the dispatch's
  * workgroups are dealt to `nranks` shards:
- *   LUMCU_SHARD_INTERLEAVED (default) the dispatch is cut into chunks of 3072 workgroups and shard r takes chunks
+ *   LUMCU_SHARD_INTERLEAVED (default) the dispatch is cut into chunks of 3072 workgroups (fewer for small dispatches,
+ *       lumcu_shard_chunk) and shard r takes chunks
  *       r, r + n, ...: every rank samples every part of the world, so the ranks finish together whatever the scene looks
  *       like (C4 at 8 ranks: all trace kernels within 0.7 % of each other);
  *   LUMCU_SHARD_CONTIGUOUS            shard r takes workgroups [T*r/n, T*(r+1)/n) of the dispatch's T: equal probe
@@ -155,6 +156,11 @@ int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, i
 #define LUMCU_SHARD_CONTIGUOUS 0
 #define LUMCU_SHARD_INTERLEAVED 1
 int lumcu_set_shard_mode(LumcuCtx *ctx, int32_t mode);
+/* The chunk size the interleaved deal of the current request list's dispatch (size) to nranks shards uses: 3072,
+ * halved for smaller dispatches until every rank gets at least 64 chunks (not below 48); 0 in contiguous mode.  It is
+ * derived from the host's view of the request count -- an upper bound after a build without a sync, the same on every
+ * rank -- so all ranks agree without talking. */
+int lumcu_shard_chunk(LumcuCtx *ctx, int32_t size, int32_t nranks, int32_t *chunk);
 int lumcu_update_shard(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift, int32_t rank, int32_t nranks);
 int lumcu_update_shard_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift);
 

@@ -85,6 +85,7 @@ SYMBOLS = {
     "lumcu_set_kernel_variant": (C.c_int, [_P, C.c_int32]),
     "lumcu_set_profiling": (C.c_int, [_P, C.c_int32]),
     "lumcu_set_shard_mode": (C.c_int, [_P, C.c_int32]),
+    "lumcu_shard_chunk": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "lumcu_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lumcu_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "lumcu_glossy": (C.c_int, [_P, C.POINTER(LumcuGlossyView), C.c_int32, C.c_int32, _P, _P, _P, _P]),
@@ -355,6 +356,11 @@ class RadianceStage:
     def set_shard_mode(self, mode):
         """SHARD_INTERLEAVED (default) or SHARD_CONTIGUOUS (lumcu_set_shard_mode)."""
         self._ck(self.lib.lumcu_set_shard_mode(self.ctx, int(mode)))
+
+    def shard_chunk(self, size, nranks):
+        ch = C.c_int32()
+        self._ck(self.lib.lumcu_shard_chunk(self.ctx, int(size), int(nranks), C.byref(ch)))
+        return ch.value
 
     def set_profiling(self, on):
         self._ck(self.lib.lumcu_set_profiling(self.ctx, int(bool(on))))

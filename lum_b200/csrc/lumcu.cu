@@ -73,8 +73,12 @@ struct Staging {
 
 }  // namespace
 
-// Interleaved sharding (UpdateArgs::il_*): chunk is a multiple of every pooled kernel's probes-per-CTA.
+// Interleaved sharding (UpdateArgs::il_*): chunks of IL_CHUNK workgroups, halved for smaller dispatches until every rank
+// gets at least 64 of them (a rank's share can be off by one chunk: 65 K probes dealt to 8 ranks in chunks of 3,072 are
+// two chunks for some ranks and three for others), never below IL_CHUNK_MIN -- every size is a multiple of every
+// pooled kernel's probes per CTA.
 constexpr int IL_CHUNK = 3072;
+constexpr int IL_CHUNK_MIN = 48;
 
 struct LumcuCtx {
     LumcuDesc desc{};
@@ -220,7 +224,7 @@ void host_direction_table(int n, std::vector<float> &out) {
 template <int R, int T, int RPT, bool DEBUG>
 int launch_pool_one(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, long long nwg) {
     constexpr int ppc = RPT * T / R;
-    static_assert(ppc >= 1 && IL_CHUNK % ppc == 0, "an interleaved chunk must hold whole CTA batches (il_map)");
+    static_assert(ppc >= 1 && IL_CHUNK_MIN % ppc == 0 && IL_CHUNK % IL_CHUNK_MIN == 0, "an interleaved chunk must hold whole CTA batches (il_map)");
     auto k = radiance_update_pool_kernel<R, T, RPT, DEBUG>;
     if (c->carveout >= 0) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, c->carveout);
     dim3 grid((unsigned)((nwg + ppc - 1) / ppc));
@@ -300,6 +304,17 @@ SceneView scene_view(LumcuCtx *c) {
     return SceneView{c->d_world, c->d_bricks, c->d_materials, c->d_mat4, c->d_field, c->wx, c->wy, c->wz, c->desc.palette_capacity,
                      c->brick0_empty ? 1 : 0, c->d_scene_flags + c->world_cur
     };
+}
+
+// chunk size of an interleaved deal of `total` workgroups to n ranks (`total` = the host's bound: the same on every rank)
+int interleave_chunk(long long total, int n) {
+    int ch = IL_CHUNK;
+    while (ch > IL_CHUNK_MIN && (long long)ch * n * 64 > total) ch /= 2;
+    return ch;
+}
+// the shard of a dispatch of `total` workgroups under the context's shard mode
+Interleave shard_of(const LumcuCtx *c, long long total, int rank, int n) {
+    return Interleave{c->shard_chunk == 0 ? 0 : interleave_chunk(total, n), rank, n};
 }
 
 // number of workgroups of [0, total) that shard `il` owns
@@ -1044,7 +1059,7 @@ int lumcu_update_shard(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shi
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
     if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
     CU(cudaEventRecord(c->ev_begin, c->stream));
-    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, Interleave{c->shard_chunk, rank, nranks})) return rc;
+    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, shard_of(c, c->nreq / size, rank, nranks))) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;
@@ -1097,7 +1112,7 @@ int lumcu_update_shard_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, in
     if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
     if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
-    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, Interleave{c->shard_chunk, c->peer_rank, c->peer_n});
+    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, shard_of(c, c->nreq / size, c->peer_rank, c->peer_n));
 }
 
 int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
@@ -1252,6 +1267,12 @@ int lumcu_set_shard_mode(LumcuCtx *c, int32_t mode) {
     if (!c) return fail(LUMCU_E_ARG, "null context");
     if (mode != LUMCU_SHARD_CONTIGUOUS && mode != LUMCU_SHARD_INTERLEAVED) return fail(LUMCU_E_ARG, "unknown shard mode %d", mode);
     c->shard_chunk = mode == LUMCU_SHARD_INTERLEAVED ? IL_CHUNK : 0;
+    return 0;
+}
+
+int lumcu_shard_chunk(LumcuCtx *c, int32_t size, int32_t nranks, int32_t *chunk) {
+    if (!c || !chunk || size < 1 || nranks < 1) return fail(LUMCU_E_ARG, "bad argument");
+    *chunk = shard_of(c, c->nreq / size, 0, nranks).chunk;
     return 0;
 }
 

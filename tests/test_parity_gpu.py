@@ -340,8 +340,9 @@ def test_interleaved_shards_compose(oracle_mod, nranks, mode):
     st.set_shard_mode(lum_b200.SHARD_INTERLEAVED if mode == "interleaved" else lum_b200.SHARD_CONTIGUOUS)
     owner = np.full(n, -1, np.int64)
     for r in range(nranks):
-        owner[D.shard_workgroups(n, r, nranks, D.SHARD_CHUNK if mode == "interleaved" else 0)] = r
+        owner[D.shard_workgroups(n, r, nranks, st.shard_chunk(1, nranks))] = r
     assert (owner >= 0).all()
+    assert st.shard_chunk(1, nranks) == (0 if mode == "contiguous" else {2: 96, 3: 96, 8: 48}[nranks])      # >= 64 chunks per rank
     for variant in (1, 0):                     # pooled and per-workgroup kernel: both map launch index -> workgroup
         st.set_kernel_variant(variant)
         union = f0.copy()
