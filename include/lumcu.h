@@ -177,6 +177,8 @@ int lumcu_free_model(LumcuCtx *ctx, int32_t model);
 
 /* The brick part of exec_copies (internal_render.cpp:1402-1446) for the blocks blockify_mesh allocated
  * (:1029-1076): for i in [0,n): bricks[dst_ids[i]] = src_ids[i] == 0 ? all-zero : bricks[src_ids[i]].
+ * The copies run concurrently: a destination may be neither a source nor named twice (LUMCU_E_ARG otherwise; the
+ * reference copies between two distinct images, and blockify's pairs satisfy this by construction: src < static <= dst).
  * Device-to-device: no brick data crosses PCIe per frame.  (The reference clears the whole atlas and
  * re-copies the static bricks; here the static bricks are never overwritten, and every dynamic brick
  * the world references is rewritten by this call, so the visible state is the same.) */
@@ -239,7 +241,7 @@ int lumcu_wait_idle(LumcuCtx *ctx);
 int lumcu_last_update_ms(LumcuCtx *ctx, float *ms);
 /* Kernel selection.  0 = one CTA per workgroup, the dispatch shape of radiance.comp itself (best for demo-sized
  * dispatches, which are latency-bound); 1 = pooled kernel, one CTA per 384 rays with lane-level ray refill (best once
- * the dispatch gives it a wave of CTAs); 2 (default) = choose by dispatch size (pooled from 8,192 workgroups on).
+ * the dispatch gives it a wave of CTAs); 2 (default) = choose by dispatch size (pooled from 6,144 workgroups on).
  * All give bit-identical results. */
 int lumcu_set_kernel_variant(LumcuCtx *ctx, int32_t variant);
 

@@ -411,8 +411,8 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
         // the z filter (unsorted special tail of a slab update) only exists in the per-workgroup kernel
         // and small dispatches (demo-sized worlds) are latency-bound: they want one workgroup per CTA
         const bool unfiltered = z_begin <= -32768 && z_end >= 32768;
-        // Which kernel (variant 2 = choose): the pooled kernel once the dispatch gives it about a wave of CTAs, i.e. from
-        // ~8 K workgroups on (B200, tools/kernel_crossover.py: 16 K probes -- pooled 0.048 / 0.098 / 0.31 ms against
+        // Which kernel (variant 2 = choose): the pooled kernel once the dispatch gives it most of a wave of CTAs, i.e. from
+        // ~6 K workgroups on (B200, tools/kernel_crossover.py: 16 K probes -- pooled 0.048 / 0.098 / 0.31 ms against
         // 0.064 / 0.115 / 0.36 at 16 / 64 / 256 rays per probe; the demo world's 2,689 probes -- 0.043 / 0.047 / 0.072
         // against 0.028 / 0.033 / 0.062).  While the real count is still on the device the last count the host has
         // seen stands in for it (poll_count); the launch itself stays sized for the bound.
@@ -421,7 +421,7 @@ int do_update(LumcuCtx *c, int time_seed, int size, int shift, long long wg_begi
             poll_count(c);
             if (c->count_hint >= 0) est = std::min(nwg, il_count(c->count_hint / size, il));
         }
-        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && est >= 8192));
+        const bool use_pool = unfiltered && (c->kernel_variant == 1 || (c->kernel_variant == 2 && est >= 6144));
         if (c->debug_flags) {
             if (c->count_on_device) return fail(LUMCU_E_STATE, "instrumented update with an unresolved request count");
             if (int rc = ensure_debug(c)) return rc;

@@ -499,7 +499,7 @@ def test_slab_update_is_jacobi_across_its_two_passes(oracle_mod, demo):
 
 
 @pytest.mark.parametrize("with_specials", [False, True], ids=["ahead", "in-place"])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])      # 2 = the library chooses, from the last count the host has seen
 def test_async_build_and_device_side_count(oracle_mod, demo, variant, with_specials):
     """lumcu_build_requests(out_count = NULL): nothing waits for the GPU, the launches are sized for an upper bound of
     the request count (14x the real one on the demo world) and the kernels stop at the count they read on the device.
