@@ -158,8 +158,8 @@ int lumcu_update_slab_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, i
 int lumcu_set_shard_mode(LumcuCtx *ctx, int32_t mode);
 /* The chunk size the interleaved deal of the current request list's dispatch (size) to nranks shards uses: 3072,
  * halved for smaller dispatches until every rank gets at least 64 chunks (not below 48); 0 in contiguous mode.  It is
- * derived from the host's view of the request count -- an upper bound after a build without a sync, the same on every
- * rank -- so all ranks agree without talking. */
+ * derived from the list's size as lumcu_set_requests gave it, or from a built list's upper bound (cells + specials) --
+ * never from the count learnt later -- so all ranks agree without talking, whichever of them has asked for its count. */
 int lumcu_shard_chunk(LumcuCtx *ctx, int32_t size, int32_t nranks, int32_t *chunk);
 int lumcu_update_shard(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift, int32_t rank, int32_t nranks);
 int lumcu_update_shard_exchange(LumcuCtx *ctx, int32_t time_seed, int32_t size, int32_t shift);
@@ -281,7 +281,10 @@ int lumcu_glossy(LumcuCtx *ctx, const LumcuGlossyView *view, int32_t width, int3
 int lumcu_glossy_device(LumcuCtx *ctx, const LumcuGlossyView *view, int32_t width, int32_t height,
                         uint64_t mat_norm_dev, uint64_t depth_dev, uint64_t frame_dev, uint64_t covered_dev);
 
-/* Interop getters: raw device addresses and the stream (cudaStream_t) as integers. */
+/* Interop getters: raw device addresses and the stream (cudaStream_t) as integers.  The world address is that of
+ * the buffer the next launches read; lumcu_upload_world_async switches to the other of its two buffers, so ask again
+ * after it.  Once the world address has been handed out the stage re-validates the world before every update (its
+ * holder may have written ids). */
 int lumcu_field_device_ptr(LumcuCtx *ctx, uint64_t *ptr);
 int lumcu_world_device_ptr(LumcuCtx *ctx, uint64_t *ptr);
 int lumcu_stream(LumcuCtx *ctx, uint64_t *stream);

@@ -123,6 +123,9 @@ struct LumcuCtx {
 
     long long nreq = 0;          // current request count -- an upper bound while count_on_device
     long long nsorted = 0;       // leading requests known to be z-sorted
+    long long shard_basis = 0;      // what the interleave chunk size is derived from: the request count as lumcu_set_requests
+                                    // gave it, or a built list's upper bound -- NOT the count learnt later, so that ranks
+                                    // agree on the chunk size whether or not one of them has asked for its count
     long long count_hint = -1;      // the last request count the host has seen (a hint for kernel choice while count_on_device)
     unsigned long long *h_count = nullptr;   // pinned: every build without a sync also queues a 16-byte copy of its count here
     cudaEvent_t ev_count = nullptr;
@@ -810,6 +813,7 @@ int lumcu_set_requests(LumcuCtx *c, const int16_t *xyzw, int64_t n) {
         c->nsorted = 0;
     }
     c->nreq = n;
+    c->shard_basis = n;
     c->count_hint = n;
     c->count_on_device = false;
     c->req_version++;
@@ -883,6 +887,7 @@ int lumcu_build_requests(LumcuCtx *c, const int16_t *special, int32_t nspecial, 
     // for the GPU.  Until somebody asks (out_count, lumcu_request_count, ...) the host works with an upper bound.
     c->count_on_device = true;
     c->nreq = std::min<long long>(c->max_requests, c->cells + nspecial);
+    c->shard_basis = c->nreq;
     c->nsorted = 0;
     c->req_version++;
     if (out_count) {
@@ -1059,7 +1064,7 @@ int lumcu_update_shard(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shi
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
     if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
     CU(cudaEventRecord(c->ev_begin, c->stream));
-    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, shard_of(c, c->nreq / size, rank, nranks))) return rc;
+    if (int rc = do_update(c, time_seed, size, shift, 0, c->nreq / size, -32768, 32768, true, shard_of(c, c->shard_basis / size, rank, nranks))) return rc;
     CU(cudaEventRecord(c->ev_end, c->stream));
     c->timed = true;
     return 0;
@@ -1112,7 +1117,7 @@ int lumcu_update_shard_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, in
     if (*c->h_status) return fail(LUMCU_E_STATE, "a peer barrier timed out earlier (a rank stopped participating)");
     if (size < 1) return fail(LUMCU_E_ARG, "size must be >= 1");
     if (c->debug_flags) if (int rc = resolve_count(c)) return rc;
-    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, shard_of(c, c->nreq / size, c->peer_rank, c->peer_n));
+    return exchange_frame(c, time_seed, size, shift, 0, c->nreq / size, false, -32768, 32768, shard_of(c, c->shard_basis / size, c->peer_rank, c->peer_n));
 }
 
 int lumcu_update_slab_exchange(LumcuCtx *c, int32_t time_seed, int32_t size, int32_t shift, int32_t z_begin, int32_t z_end) {
@@ -1272,7 +1277,7 @@ int lumcu_set_shard_mode(LumcuCtx *c, int32_t mode) {
 
 int lumcu_shard_chunk(LumcuCtx *c, int32_t size, int32_t nranks, int32_t *chunk) {
     if (!c || !chunk || size < 1 || nranks < 1) return fail(LUMCU_E_ARG, "bad argument");
-    *chunk = shard_of(c, c->nreq / size, 0, nranks).chunk;
+    *chunk = shard_of(c, c->shard_basis / size, 0, nranks).chunk;
     return 0;
 }
 

@@ -1,17 +1,21 @@
-"""Multi-GPU plumbing of the radiance stage: probe sharding by z-slab + per-frame field exchange.
+"""Multi-GPU plumbing of the radiance stage: probe sharding + per-frame field exchange.
 
-Design (SURVEY.md section 8e): the read-only world / palette / materials are replicated on every
-rank; the field is replicated too and updated Jacobi-style.  Rank r of N owns the contiguous
-z-slab [r*Z/N, (r+1)*Z/N) of the field (the field is z-major, so a slab is one contiguous range of
-words), updates exactly the probes of that slab (lumcu_update_slab) and then all ranks exchange
-their slabs -- either with ONE in-place all-gather (all_gather_field), or fused into the commit itself:
-lumcu_update_slab_exchange stores every new texel straight into all ranks' field replicas over NVLink
-peer memory between two flag barriers (open_peer_exchange wires it) -- after which every rank holds the
-identical new field for the next frame's gathers.  With the fused exchange a rank's texels need not be contiguous
-in the field, so the sharding there is by workgroup index (lumcu_update_shard_exchange): INTERLEAVED chunks of
-SHARD_CHUNK workgroups by default (every rank samples every part of the world, so the ranks finish together whatever
-the scene looks like), or CONTIGUOUS equal ranges of the dispatch (lumcu_set_shard_mode).  torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on
-CPU for the tests of this host-side logic).
+Design (SURVEY.md section 8e, DESIGN.md section 6): the read-only world / palette / materials are replicated on every
+rank; the field is replicated too and updated Jacobi-style, so probes shard with one exchange per frame and N ranks
+compute bit-identically to one (seeds use the global workgroup index).
+
+* NCCL baseline: rank r of N owns the contiguous z-slab [r*Z/N, (r+1)*Z/N) of the field (the field is z-major, so a
+  slab is one contiguous range of words), updates exactly the probes of that slab (lumcu_update_slab) and all ranks
+  exchange their slabs with ONE in-place all-gather (all_gather_field).
+* Peer exchange (open_peer_exchange wires it; the default of bench.py): lumcu_update_shard_exchange shards the
+  dispatch by workgroup index -- INTERLEAVED chunks by default (every rank samples every part of the world, so the
+  ranks finish together whatever the scene looks like; chunk size: stage.shard_chunk), or CONTIGUOUS equal ranges
+  (lumcu_set_shard_mode) -- traces into the rank's own staging array, publishes its arrival in every rank's flag array
+  and then reads every texel of the dispatch from its owner's staging array over NVLink into the local field: one
+  flag barrier and one gather/commit kernel per frame, no collective call.  lumcu_update_slab_exchange does the same
+  for z-slabs with the transfer as a push from the trace kernel.
+
+torch.distributed is plumbing only (NCCL over NVLink on GPUs; gloo on CPU for the tests of this host-side logic).
 """
 from __future__ import annotations
 
@@ -83,9 +87,9 @@ def device_tensor_view(ptr: int, nwords: int, device):
 
 
 def open_peer_exchange(stage, rank: int, world_size: int, device=None, group=None):
-    """Wire the fused commit+exchange (lumcu_update_slab_exchange): export this rank's IPC blob,
+    """Wire the peer exchange (lumcu_update_shard_exchange / lumcu_update_slab_exchange): export this rank's IPC blob,
     all-gather the blobs through torch.distributed (NCCL: a small uint8 device tensor; gloo: CPU) and
-    open the peers' field / flag buffers.  Every rank must call it (collective)."""
+    open the peers' staging / flag buffers.  Every rank must call it (collective)."""
     import numpy as np
     import torch
     import torch.distributed as dist
