@@ -42,6 +42,27 @@ def shard_count(nwg: int, rank: int, world_size: int, chunk: int = SHARD_CHUNK) 
     return (full // world_size) * chunk + (chunk if full % world_size > rank else 0) + (rem if full % world_size == rank else 0)
 
 
+def shard_owner(nwg: int, world_size: int, chunk: int = SHARD_CHUNK):
+    """owner[w] = the rank whose shard holds workgroup w -- what gather_commit_kernel evaluates to know whose staging
+    array to read the texel of w from.  Interleaved: (w // chunk) % n.  Contiguous (chunk == 0): the number of shard
+    boundaries nwg*k//n (k = 1..n-1) that are <= w."""
+    import numpy as np
+    w = np.arange(nwg, dtype=np.int64)
+    if chunk == 0:
+        bounds = np.array([nwg * k // world_size for k in range(1, world_size)], np.int64)
+        return np.searchsorted(bounds, w, side="right")
+    return (w // chunk) % world_size
+
+
+def interleave_chunk(total: int, world_size: int) -> int:
+    """The chunk size lumcu_update_shard_exchange deals a dispatch of `total` workgroups out in (lumcu_shard_chunk):
+    3072, halved until every rank gets at least 64 chunks, not below 48."""
+    ch = SHARD_CHUNK
+    while ch > 48 and ch * world_size * 64 > total:
+        ch //= 2
+    return ch
+
+
 def slab_bounds(wz: int, rank: int, world_size: int):
     """z range [z0, z1) owned by `rank`.  Requires wz % world_size == 0 (16 and 64 both divide by 8)."""
     if wz % world_size:

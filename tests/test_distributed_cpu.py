@@ -40,6 +40,12 @@ def test_interleaved_shard_arithmetic(nwg, world):
         assert np.all(np.diff(idx) > 0)
         seen[idx] += 1
     assert np.all(seen == 1)
+    for ch in (D.SHARD_CHUNK, 0, 48):
+        own = D.shard_owner(nwg, world, ch)
+        for r in range(world):
+            assert np.array_equal(np.nonzero(own == r)[0], D.shard_workgroups(nwg, r, world, ch))
+    ch = D.interleave_chunk(nwg, world)
+    assert ch % 48 == 0 and (ch == 48 or ch * world * 64 <= nwg) and (ch == D.SHARD_CHUNK or 2 * ch * world * 64 > nwg)
     sizes = [D.shard_count(nwg, r, world) for r in range(world)]
     assert max(sizes) - min(sizes) <= D.SHARD_CHUNK
 
@@ -100,9 +106,13 @@ def test_two_rank_gloo_matches_single_rank(tmp_path):
     assert np.array_equal(a, f)          # and it is the single-rank result
 
 
-def _shard_worker(rank, world, port, frames, out_dir):
-    """Interleaved shards + a texel-wise exchange (what commit_peers_kernel does with peer stores, here as an
-    all_gather of (cell, word) pairs).  A small chunk makes the demo's 2,692 workgroups span several chunks."""
+def _shard_worker(rank, world, port, frames, out_dir, chunk):
+    """The frame of lumcu_update_shard_exchange with gloo in the place of NVLink: every rank traces its shard
+    (interleaved chunks, or contiguous ranges for chunk == 0) into its OWN staging array indexed by workgroup, the
+    staging arrays are exchanged (the kernel reads them in place over peer memory; here an all_gather), and every rank
+    commits the WHOLE dispatch locally, taking the texel of workgroup w from the staging array of w's owner
+    (D.shard_owner, the arithmetic of gather_commit_kernel).  A small chunk makes the demo's 2,692 workgroups span
+    several chunks."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -111,30 +121,34 @@ def _shard_worker(rank, world, port, frames, out_dir):
     sc = O.Scene(d["world"], d["bricks"], d["materials"])
     sp = np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16)
     req = O.build_requests(d["world"], sp)
-    mine = D.shard_workgroups(len(req), rank, world, chunk=384)
+    nwg = len(req)
+    mine = D.shard_workgroups(nwg, rank, world, chunk=chunk)
+    owner = D.shard_owner(nwg, world, chunk)
+    assert np.array_equal(np.nonzero(owner == rank)[0], mine)
     cell = req[:, 0].astype(np.int64) + sc.wx * (req[:, 1].astype(np.int64) + sc.wy * req[:, 2].astype(np.int64))
     field = np.zeros(sc.cells, np.uint32)
     for f in range(frames):
-        new = field.copy()
+        staged = np.full(nwg, 0xDEADBEEF, np.uint32)                      # only this rank's workgroups get written
         runs = np.split(mine, np.nonzero(np.diff(mine) != 1)[0] + 1) if len(mine) else []
         for run in runs:
             r = O.update(sc, field, req, f, wg_range=(int(run[0]), int(run[-1]) + 1), nthreads=2)
-            new[cell[run]] = r["field"][cell[run]]
-        pairs = [None] * world
-        dist.all_gather_object(pairs, (cell[mine], new[cell[mine]]))
-        for c, w in pairs:
-            field[c] = w
+            staged[run] = r["field"][cell[run]]
+        all_staged = [None] * world
+        dist.all_gather_object(all_staged, staged)
+        stacked = np.stack(all_staged)
+        field[cell] = stacked[owner, np.arange(nwg)]                      # gather from the owner + commit, whole dispatch
     np.save(os.path.join(out_dir, f"shard_{rank}.npy"), field)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_interleaved_shards_match_single_rank(tmp_path):
+@pytest.mark.parametrize("chunk", [384, 0], ids=["interleaved", "contiguous"])
+def test_two_rank_gloo_interleaved_shards_match_single_rank(tmp_path, chunk):
     import oracle as O
     frames = 3
     port = _free_port()
-    mp.spawn(_shard_worker, args=(2, port, frames, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_shard_worker, args=(2, port, frames, str(tmp_path), chunk), nprocs=2, join=True)
     d = scenes.demo_scene()
     sc = O.Scene(d["world"], d["bricks"], d["materials"])
     req = O.build_requests(d["world"], np.array([(7, 9, 2, 0), (40, 40, 14, 0), (6, 8, 1, 0)], np.int16))

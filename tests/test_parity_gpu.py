@@ -344,6 +344,7 @@ def test_interleaved_shards_compose(oracle_mod, nranks, mode):
     assert (owner >= 0).all()
     # >= 64 chunks per rank, from the built list's upper bound (23,040 cells + 2 specials), not the count asked for above
     assert st.shard_chunk(1, nranks) == (0 if mode == "contiguous" else {2: 96, 3: 96, 8: 48}[nranks])
+    assert mode == "contiguous" or st.shard_chunk(1, nranks) == D.interleave_chunk(st.cells + 2, nranks)   # the Python mirror
     for variant in (1, 0):                     # pooled and per-workgroup kernel: both map launch index -> workgroup
         st.set_kernel_variant(variant)
         union = f0.copy()
