@@ -129,9 +129,12 @@ extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capaci
                                               const int16_t *world, const uint8_t *bricks, const float *materials,
                                               uint32_t *replicas, int nranks, int il_chunk,
                                               const int16_t *requests, long long nreq, int time_seed, int size, int shift,
-                                              const float *table, const float *sun3, int variant, int frames, int push) {
+                                              const float *table, const float *sun3, int variant, int frames, int push, long long slack) {
     if (nranks < 1 || nranks > MAX_PEERS) return -1;
-    const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? nreq / size : 0;
+    // slack > 0: every rank only knows an upper bound of the request count (a list built without a sync): launches and
+    // shard chunks follow the bound, the kernels cut the dispatch down to the count they read from "device" memory
+    const unsigned long long count = (unsigned long long)nreq;
+    const long long cells = (long long)wx * wy * wz, nwg_all = size > 0 ? (nreq + slack) / size : 0;
     const size_t half = (size_t)std::max<long long>(nwg_all, 1);
     std::vector<std::vector<uint32_t>> staged((size_t)nranks, std::vector<uint32_t>(2 * half, 0xDEADBEEFu));
     std::vector<std::vector<unsigned>> flags((size_t)nranks, std::vector<unsigned>(MAX_PEERS, 0u));
@@ -147,7 +150,7 @@ extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capaci
             const long long traced = trace_on_host(wx, wy, wz, capacity, brick0_empty, R, reactiveness, world, bricks, materials,
                                                    replicas + (size_t)r * cells, requests, nreq, time_seed + f, size, shift, table, sun3,
                                                    variant, Interleave{il_chunk, r, nranks}, staged[r].data() + parity * half,
-                                                   nullptr, nullptr, nullptr, tot, push ? &inbox : nullptr);
+                                                   nullptr, nullptr, nullptr, tot, push ? &inbox : nullptr, slack);
             if (traced < 0) return -1;
             PeerFlags pf{};
             pf.n = nranks; pf.rank = r;
@@ -161,12 +164,13 @@ extern "C" int kernels_on_host_update_sharded(int wx, int wy, int wz, int capaci
             if (push)
                 emu_launch((unsigned)((nwg_all + ct - 1) / ct), 1, ct, [&] {
                     commit_kernel(replicas + (size_t)r * cells, staged[r].data() + parity * half, reinterpret_cast<const short4 *>(requests),
-                                  0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, Interleave{il_chunk, 0, 1}, nullptr, xw);
+                                  0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, Interleave{il_chunk, 0, 1}, slack > 0 ? &count : nullptr, xw);
                 });
             else
                 emu_launch(3, 1, ct, [&] {                          // a persistent grid: 3 CTAs stride over the dispatch
                     gather_commit_kernel(replicas + (size_t)r * cells, ShardSources{inbox, il_chunk, nranks},
-                                         reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz, nullptr, xw);
+                                         reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz,
+                                         slack > 0 ? &count : nullptr, xw);
                 });
         }
     }

@@ -253,10 +253,11 @@ def test_slab_bound_kernel(emu, oracle_mod, demo):
             assert (int(out[0]), int(out[1])) == (int(np.searchsorted(zs, zb, "left")), int(np.searchsorted(zs, ze, "left")))
 
 
+@pytest.mark.parametrize("slack", [0, 31], ids=["count-known", "count-on-device"])
 @pytest.mark.parametrize("push", [0, 1], ids=["pull", "push"])
 @pytest.mark.parametrize("chunk", [12, 0], ids=["interleaved", "contiguous"])
 @pytest.mark.parametrize("nranks,variant", [(2, POOL), (3, POOL), (2, WG)])
-def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant, chunk, push):
+def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nranks, variant, chunk, push, slack):
     """SURVEY 8e on the emulator: three frames dealt to `nranks` ranks (contiguous shards or interleaved chunks, il_map /
     shard_window in the kernels), arrive_kernel, then the transfer -- pull: gather_commit_kernel reads every texel from its
     owner's staged[] (alternating halves); push: the trace stored into every rank's inbox and commit_kernel scatters locally
@@ -264,6 +265,7 @@ def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nrank
     O = oracle_mod
     sc = scene_of(O, small_synth)
     req = np.ascontiguousarray(O.build_requests(small_synth["world"])[::53][:45], np.int16)      # 45 probes, chunks of 12
+    req_buf = np.zeros((len(req) + slack, 4), np.int16); req_buf[:len(req)] = req                 # the list buffer holds the bound
     f0 = np.random.default_rng(8).integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
     ref = f0
     for f in range(3):
@@ -279,8 +281,8 @@ def test_interleaved_shards_with_peer_commit(emu, oracle_mod, small_synth, nrank
     emu.kernels_on_host_update_sharded.restype = C.c_int
     rc = emu.kernels_on_host_update_sharded(C.c_int(wx), C.c_int(wy), C.c_int(wz), C.c_int(bricks.shape[0]), C.c_int(1),
                                             C.c_int(64), C.c_float(0.01), p(world), p(bricks), p(mats), p(replicas),
-                                            C.c_int(nranks), C.c_int(chunk), p(req), C.c_longlong(len(req)), C.c_int(4),
-                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant), C.c_int(3), C.c_int(push))
+                                            C.c_int(nranks), C.c_int(chunk), p(req_buf), C.c_longlong(len(req)), C.c_int(4),
+                                            C.c_int(1), C.c_int(0), p(table), p(sun), C.c_int(variant), C.c_int(3), C.c_int(push), C.c_longlong(slack))
     assert rc == 0
     for r in range(nranks):
         assert np.array_equal(replicas[r], ref), r
