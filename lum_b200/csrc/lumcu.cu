@@ -136,6 +136,7 @@ struct LumcuCtx {
     int sm_count = 148;          // cudaDevAttrMultiProcessorCount (grid sizing of the grid-stride kernels)
     int pool_threads = 128;      // tuning knobs (env LUMCU_POOL_THREADS / LUMCU_CARVEOUT, read at create)
     int carveout = -1;
+    bool vec_commit = true;      // env LUMCU_VEC_COMMIT=0: the element-wise commit kernel for the plain update too (A/B runs)
     int shard_chunk = IL_CHUNK;  // lumcu_set_shard_mode: IL_CHUNK = interleaved chunks (default), 0 = contiguous shards
     int kernel_variant = 2;      // 0 = one workgroup per CTA (radiance.comp's own shape), 1 = pooled, 2 = auto
     bool brick0_empty = true;    // device bricks start zeroed; tracked by lumcu_upload_bricks
@@ -375,6 +376,15 @@ int commit_local(LumcuCtx *c, int size, int shift, long long wg_begin, long long
     if (nwg <= 0) return 0;
     if (int rc = before_field_write(c)) return rc;
     const int ct = 256;
+    if (c->vec_commit && il.n <= 1 && !xw.flags && parity == 0 && size == 1 && shift == 0 && wg_begin == 0 && z_begin <= -32768 && z_end >= 32768) {
+        // the plain full update: four workgroups per thread, 16-byte stores where four requests are four adjacent texels
+        const long long threads = (wg_end + 3) / 4;
+        commit_vec4_kernel<<<(unsigned)((threads + ct - 1) / ct), ct, 0, c->stream>>>(c->d_field, staged_half(c, parity), c->d_requests, wg_end,
+                                                                                   c->wx, c->wy, c->wz, count_ptr(c));
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     commit_kernel<<<(unsigned)((nwg + ct - 1) / ct), ct, 0, c->stream>>>(
         c->d_field, staged_half(c, parity), c->d_requests, wg_begin, wg_end, size, shift, c->wx, c->wy, c->wz, z_begin, z_end, il,
         count_ptr(c), xw);
@@ -545,6 +555,7 @@ int lumcu_create(const LumcuDesc *d, LumcuCtx **out) {
     if (const char *e = getenv("LUMCU_POOL_THREADS")) c->pool_threads = atoi(e) == 256 ? 256 : 128;
     if (const char *e = getenv("LUMCU_CARVEOUT")) c->carveout = atoi(e);
     if (const char *e = getenv("LUMCU_KERNEL_VARIANT")) c->kernel_variant = atoi(e);
+    if (const char *e = getenv("LUMCU_VEC_COMMIT")) c->vec_commit = atoi(e) != 0;
     if (const char *e = getenv("LUMCU_SHARD_MODE")) c->shard_chunk = atoi(e) == LUMCU_SHARD_CONTIGUOUS ? 0 : IL_CHUNK;
     host_direction_table(R, c->h_table);
     CUB(cudaMemcpyAsync(c->d_table, c->h_table.data(), (size_t)R * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));

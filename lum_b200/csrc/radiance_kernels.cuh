@@ -566,6 +566,35 @@ __global__ void commit_kernel(uint32_t *__restrict__ field, const uint32_t *__re
         field[rq.x + wx * (rq.y + wy * rq.z)] = __ldcv(staged + w);      // written by peers: not through a stale L1 line
 }
 
+// The same scatter for the plain single-GPU update of a full dispatch (size 1, no shard, no z filter), four workgroups
+// per thread: the request rule emits probes in z,y,x order, so four consecutive requests are almost always four
+// x-adjacent texels -- one 16-byte store where they are, and aligned; element by element where not (row ends, specials,
+// probes outside the world).  (north_star: "coalesced vectorised stores into the radiance field".)
+__global__ void commit_vec4_kernel(uint32_t *__restrict__ field, const uint32_t *__restrict__ staged,
+                                   const short4 *__restrict__ requests, long long wg_end, int wx, int wy, int wz,
+                                   const unsigned long long *__restrict__ nreq_dev) {
+    if (nreq_dev) { const long long n = device_workgroups(nreq_dev, 1); wg_end = n < wg_end ? n : wg_end; }
+    const long long w0 = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (w0 >= wg_end) return;
+    if (w0 + 3 < wg_end) {
+        const uint4 q01 = reinterpret_cast<const uint4 *>(requests + w0)[0], q23 = reinterpret_cast<const uint4 *>(requests + w0)[1];
+        const uint4 v = *reinterpret_cast<const uint4 *>(staged + w0);
+        // a request = (x, y, z, w) as four int16: x | y << 16 in the first word, z in the low half of the second
+        const int x0 = (short)(q01.x & 0xffffu), y0 = (short)(q01.x >> 16), z0 = (short)(q01.y & 0xffffu);
+        const bool row = q01.z == q01.x + 1u && q23.x == q01.x + 2u && q23.z == q01.x + 3u &&            // x, x+1, x+2, x+3, same y
+                         (q01.w & 0xffffu) == (q01.y & 0xffffu) && (q23.y & 0xffffu) == (q01.y & 0xffffu) && (q23.w & 0xffffu) == (q01.y & 0xffffu);
+        if (row && x0 >= 0 && x0 + 3 < wx && (unsigned)y0 < (unsigned)wy && (unsigned)z0 < (unsigned)wz) {
+            const long long c0 = x0 + (long long)wx * (y0 + (long long)wy * z0);
+            if ((c0 & 3) == 0) { *reinterpret_cast<uint4 *>(field + c0) = v; return; }
+        }
+    }
+    for (long long w = w0; w < wg_end && w < w0 + 4; w++) {
+        const short4 rq = requests[w];
+        if ((unsigned)rq.x < (unsigned)wx && (unsigned)rq.y < (unsigned)wy && (unsigned)rq.z < (unsigned)wz)
+            field[rq.x + wx * (rq.y + wy * rq.z)] = staged[w];
+    }
+}
+
 // ---- the exchange as a PULL: all-gather and commit in one kernel ------------------------------------------------
 // lumcu_update_shard_exchange: every rank traces its shard into its OWN staged[] (nothing remote in the trace kernel:
 // fine-grained peer stores from its last phase cost the trace 2 % at 8 ranks), publishes its arrival, and then this

@@ -1,6 +1,7 @@
 // kernels_on_host.cpp -- TEST INFRASTRUCTURE ONLY (see simt_emu.hpp).
 // The radiance update as lumcu.cu's do_update() launches it -- trace kernel (pooled or one workgroup per CTA), then the
 // commit kernel -- with the kernels of lum_b200/csrc/radiance_kernels.cuh themselves running on the host emulator.
+#include <cstring>
 #include "simt_emu.hpp"
 #include "../../lum_b200/csrc/radiance_kernels.cuh"
 
@@ -106,6 +107,21 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
     for (long long i = 0; i < cells; i++) field_new[i] = field_old[i];
     if (nwg == 0) return 0;
     const int ct = 64;
+    if (size == 1 && shift == 0 && il_n == 1) {
+        // the plain full update commits through commit_vec4_kernel, as lumcu.cu's commit_local does (16-byte accesses:
+        // the list goes into a 16-byte-aligned copy, a numpy slice need not be)
+        std::vector<uint4> aligned((size_t)(nwg_all + 1) / 2 + 1);
+        std::memcpy(aligned.data(), requests, (size_t)nwg_all * sizeof(short4));
+        std::vector<uint4> field_al((size_t)(cells + 3) / 4);
+        std::memcpy(field_al.data(), field_new, (size_t)cells * 4);
+        const long long threads = (nwg_all + 3) / 4;
+        emu_launch((unsigned)((threads + ct - 1) / ct), 1, ct, [&] {
+            commit_vec4_kernel(reinterpret_cast<uint32_t *>(field_al.data()), staged.data(), reinterpret_cast<const short4 *>(aligned.data()),
+                               nwg_all, wx, wy, wz, slack > 0 ? &count : nullptr);
+        });
+        std::memcpy(field_new, field_al.data(), (size_t)cells * 4);
+        return 0;
+    }
     emu_launch((unsigned)((nwg + ct - 1) / ct), 1, ct, [&] {
         commit_kernel(field_new, staged.data(), reinterpret_cast<const short4 *>(requests), 0, nwg_all, size, shift, wx, wy, wz, -32768, 32768, il,
                       slack > 0 ? &count : nullptr, ExchangeWait{});
