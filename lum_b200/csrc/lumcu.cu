@@ -245,12 +245,8 @@ int launch_update_pool(LumcuCtx *c, const SceneView &sv, const UpdateArgs &a, lo
     switch (c->R) {
         case 16: return launch_pool_one<16, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         case 32: return launch_pool_one<32, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
-#ifdef LUMCU_T192        // tuning build (tools/final_sweep.sh): six warps with 64-ray slices, 7 CTAs per SM, twice the L1
-        case 64: return launch_pool_one<64, 192, 2, DEBUG>(c, sv, a, nwg);
-#else
         case 64: return c->pool_threads == 128 ? launch_pool_one<64, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg)
                                                : launch_pool_one<64, 256, 4, DEBUG>(c, sv, a, nwg);
-#endif
         case 128: return launch_pool_one<128, 128, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         case 256: return launch_pool_one<256, 256, LUMCU_RPT, DEBUG>(c, sv, a, nwg);
         default: return fail(LUMCU_E_ARG, "rays_per_probe %d unsupported", c->R);

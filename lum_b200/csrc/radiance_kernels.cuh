@@ -216,32 +216,10 @@ struct PoolShared {
 // than the CTA-wide pool; the stragglers are balanced across warps by the tail passes anyway).
 // FAST: march_step_fast (validated scene); a ray that ends without a hit stores -t_pre ("pending", see
 // resolve_pending), otherwise -t.
-// Tuning knobs of the refill (tools/final_sweep.sh builds them side by side; the defaults are what ships):
-//   LUMCU_REFILL_MIN  a warp refills its idle lanes only once at least this many are idle (1 = as soon as one is): the
-//                     refill block is ~35 warp-instructions at half-empty lanes, run in three of four loop iterations;
-//   LUMCU_COHERE      pass 0 of a full batch hands out its slots ray-major instead of probe-major -- the lanes of a warp
-//                     then hold the same few ray indices (i.e. nearly parallel directions) of the batch's x-adjacent
-//                     probes, whose world fetches share sectors; 1 = ray indices ascending, 2 = the even indices, then
-//                     the odd (negated) ones, 3 = by polar angle of the cast direction.  A permutation of the schedule only.
-#ifndef LUMCU_REFILL_MIN
-#define LUMCU_REFILL_MIN 1
-#endif
-#ifndef LUMCU_COHERE
-#define LUMCU_COHERE 0
-#endif
-template <int R, int PPC>
-__device__ __forceinline__ int cohere_slot(int pos) {
-    const int q = pos / PPC, pr = pos - q * PPC;                    // position = (ray-order index, probe), probe fastest
-    const int ray = LUMCU_COHERE == 2 ? ((q % (R / 2)) * 2 + q / (R / 2))      // 0, 2, 4, ... then 1, 3, 5, ...
-                  : LUMCU_COHERE == 3 ? ((q & 1) ? R - q : q)                  // 0, R-1, 2, R-3, ...: sorted by the polar angle of
-                  : q;                                                         // the direction actually cast (odd rays are negated)
-    return pr * R + ray;
-}
-
-template <int NR, int PARK, bool DEBUG, bool PRIVATE, bool FAST, int R = 0, int PPC = 0>
+template <int NR, int PARK, bool DEBUG, bool PRIVATE, bool FAST>
 __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const SceneView &s, const MarchConsts &mc,
                                            int *next, int first, const unsigned short *src, int limit,
-                                           unsigned short *dst, int *dst_count, bool can_park, int lane, bool cohere = false) {
+                                           unsigned short *dst, int *dst_count, bool can_park, int lane) {
     constexpr unsigned FULL = 0xffffffffu;
     const uint3 wsbits = {__float_as_uint(mc.wsx), __float_as_uint(mc.wsy), __float_as_uint(mc.wsz)};
     int cur = -1;
@@ -251,7 +229,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
     for (;;) {
         unsigned idle = __ballot_sync(FULL, cur < 0);
         if (idle) {
-            if (!exhausted && (LUMCU_REFILL_MIN <= 1 || __popc(idle) >= LUMCU_REFILL_MIN)) {
+            if (!exhausted) {
                 const int cnt = __popc(idle);
                 int base = mine;
                 if constexpr (PRIVATE) {
@@ -263,8 +241,7 @@ __device__ __forceinline__ void pool_march(PoolShared<NR, DEBUG> &sm, const Scen
                 if (cur < 0) {
                     const int pos = base + __popc(idle & ((1u << lane) - 1u));
                     if (pos < limit) {
-                        if constexpr (PRIVATE && LUMCU_COHERE != 0 && PPC > 0) cur = cohere ? cohere_slot<R, PPC>(pos) : pos;
-                        else cur = src ? (int)src[pos] : pos;
+                        cur = src ? (int)src[pos] : pos;
                         sm.load(cur, q);
                     }
                 }
@@ -425,8 +402,7 @@ __device__ __forceinline__ void pool_cta_body(PoolCta<R, THREADS, RPT, DEBUG> &c
     const MarchConsts mc = {(float)s.wx * 16.0f, (float)s.wy * 16.0f, (float)s.wz * 16.0f};
     {   // warp w owns slots [w*NR/NW, (w+1)*NR/NW) of the batch
         const int first = warp * (NR / NW), last = min(nrays, first + NR / NW);
-        pool_march<NR, PARK, DEBUG, true, FAST, R, PPC>(sm, s, mc, nullptr, first, nullptr, last, sm_list[0], &sm_park[0], NW > 1, lane,
-                                                        nprobes == PPC);      // (LUMCU_COHERE: a ragged last batch keeps slot order)
+        pool_march<NR, PARK, DEBUG, true, FAST>(sm, s, mc, nullptr, first, nullptr, last, sm_list[0], &sm_park[0], NW > 1, lane);
     }
     __syncthreads();
     const int parked0 = sm_park[0];

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """A tuning build's kernels on the host SIMT emulator against the oracle (no GPU): the pooled kernel compiled with the
 given -D flags runs full and ragged batches of a dense world at 16 / 64 / 256 rays per probe and of the demo world.
-usage: emu_check_variant.py LUMCU_COHERE=1 LUMCU_REFILL_MIN=4 ..."""
+usage: emu_check_variant.py LUMCU_PARK=6 LUMCU_TAILDIV=64 ..."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
