@@ -10,10 +10,12 @@ sys.path.insert(0, ROOT)
 import lum_b200
 from lum_b200 import scenes
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "sweep"
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+tag = args[0] if args else "sweep"
+NO_ENV = "--no-env" in sys.argv       # builds only (the run-time knobs are in profiles/r02_final_sweep.md already)
 out = os.path.join(ROOT, "gpurun_out", tag)
 os.makedirs(out, exist_ok=True)
-STEPS = 8
+STEPS = 6
 
 
 def bind(path):
@@ -34,7 +36,7 @@ for line in open(os.path.join(ROOT, "tools", "final_variants.txt")):
     if os.path.exists(p):
         cands.append((n, p, {"flags": f}))
 base_lib = cands[0][1]
-for env in ({"LUMCU_CARVEOUT": "50"}, {"LUMCU_CARVEOUT": "65"}, {"LUMCU_CARVEOUT": "100"}, {"LUMCU_POOL_THREADS": "256"},
+for env in () if NO_ENV else ({"LUMCU_CARVEOUT": "50"}, {"LUMCU_CARVEOUT": "65"}, {"LUMCU_CARVEOUT": "100"}, {"LUMCU_POOL_THREADS": "256"},
             {"LUMCU_KERNEL_VARIANT": "0"}):
     cands.append(("env " + " ".join(f"{k}={v}" for k, v in env.items()), base_lib, env))
 
@@ -85,8 +87,13 @@ if best["name"] != "shipped" and res["gain"] > 0.015 and best["field_xor"] == ba
     env = dict(os.environ, **best["env"])
     if best["lib"] != "liblumcu.so":
         env["LUMCU_LIB"] = os.path.join(ROOT, "lum_b200", best["lib"])
-    t = time.time()
-    p = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q"], cwd=ROOT, env=env, capture_output=True, text=True)
-    tail = "\n".join(p.stdout.strip().splitlines()[-6:])
-    open(os.path.join(out, "parity.log"), "w").write(f"# GPU test-suite on {best['name']} (rc {p.returncode}, {time.time() - t:.0f} s)\n{tail}\n")
-    print(open(os.path.join(out, "parity.log")).read())
+    # the parity tests proper first (without the whole-C4 test), then the whole-C4 test, then the rest: a call that runs out
+    # of time still leaves the most important verdicts behind
+    for sel in (["tests/test_parity_gpu.py", "-k", "not full_size"], ["tests/test_parity_gpu.py", "-k", "full_size"],
+                ["tests", "--deselect", "tests/test_parity_gpu.py"]):
+        t = time.time()
+        p = subprocess.run([sys.executable, "-m", "pytest", *sel, "-m", "gpu", "-q", "-x"], cwd=ROOT, env=env, capture_output=True, text=True)
+        tail = "\n".join(p.stdout.strip().splitlines()[-4:])
+        with open(os.path.join(out, "parity.log"), "a") as f:
+            f.write(f"# {best['name']}: pytest {' '.join(sel)} -m gpu (rc {p.returncode}, {time.time() - t:.0f} s)\n{tail}\n")
+        print(tail, flush=True)
