@@ -9,14 +9,15 @@ A step = one full radiance-field update: every probe selected by Lum's request r
 Workloads (config.workload):
   synthetic-256x256x64  BASELINE.json configs[3] (SURVEY.md 8d "C4"): the configuration the metric
                         is quoted on at 1/2/4/8 GPUs; fits one GPU, so it is the workload at every N
-                        (strong scaling: total work fixed, probes sharded by z-slab, all-gather of
-                        the field each step).  DEFAULT.
+                        (strong scaling: total work fixed, the dispatch's probes dealt to the ranks in
+                        interleaved chunks, the new texels gathered by every rank each step).  DEFAULT.
   demo                  BASELINE.json configs[1]: Lum's demo world, full recompute (2,689 probes).
                         Also measured at N=1 in the default run and reported under "demo".
 
 Timed regions (CUDA events on the stage's stream, L2 flushed between timed steps, max over ranks):
-  value  inputs resident in HBM: update kernel(s) + commit; when N > 1 the commit IS the exchange (peer
-         stores over NVLink between two flag barriers; --exchange nccl = update + NCCL all-gather)
+  value  inputs resident in HBM: update kernel(s) + commit; when N > 1 the commit IS the exchange (one flag
+         barrier, then one kernel reads every texel from its owner's staging array over NVLink and stores
+         it locally; --exchange nccl = z-slab update + NCCL all-gather of the field)
   e2e    through the C-ABI with HOST buffers: world upload (pinned staging) + device request-list
          build + update (+ all-gather) + field download
 The oracle (oracle/) is used here only for the cpu_baseline leg and --impl reference.
