@@ -129,6 +129,36 @@ extern "C" int kernels_on_host_update(int wx, int wy, int wz, int capacity, int 
     return 0;
 }
 
+// The store side alone: staged[w] -> field at request w, through commit_vec4_kernel (vec != 0) or commit_kernel, for a
+// hand-made list.  count_slack > 0: the launch is sized for nreq + count_slack and cut down to the device-side count.
+extern "C" int kernels_on_host_commit(int wx, int wy, int wz, const int16_t *requests, long long nreq, const uint32_t *staged_in,
+                                      uint32_t *field, int vec, long long count_slack) {
+    const long long cells = (long long)wx * wy * wz, bound = nreq + count_slack;
+    const unsigned long long count = (unsigned long long)nreq;
+    std::vector<uint4> req_al((size_t)(bound + 1) / 2 + 1, make_uint4(0u, 0u, 0u, 0u));       // 16-byte aligned, as cudaMalloc gives
+    std::memcpy(req_al.data(), requests, (size_t)nreq * sizeof(short4));
+    std::vector<uint4> staged_al((size_t)(bound + 3) / 4 + 1, make_uint4(0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu));
+    std::memcpy(staged_al.data(), staged_in, (size_t)nreq * 4);
+    std::vector<uint4> field_al((size_t)(cells + 3) / 4);
+    std::memcpy(field_al.data(), field, (size_t)cells * 4);
+    const int ct = 64;
+    if (vec) {
+        const long long threads = (bound + 3) / 4;
+        emu_launch((unsigned)((threads + ct - 1) / ct), 1, ct, [&] {
+            commit_vec4_kernel(reinterpret_cast<uint32_t *>(field_al.data()), reinterpret_cast<const uint32_t *>(staged_al.data()),
+                               reinterpret_cast<const short4 *>(req_al.data()), bound, wx, wy, wz, count_slack > 0 ? &count : nullptr);
+        });
+    } else {
+        emu_launch((unsigned)((bound + ct - 1) / ct), 1, ct, [&] {
+            commit_kernel(reinterpret_cast<uint32_t *>(field_al.data()), reinterpret_cast<const uint32_t *>(staged_al.data()),
+                          reinterpret_cast<const short4 *>(req_al.data()), 0, bound, 1, 0, wx, wy, wz, -32768, 32768,
+                          Interleave{IL_CHUNK, 0, 1}, count_slack > 0 ? &count : nullptr, ExchangeWait{});
+        });
+    }
+    std::memcpy(field, field_al.data(), (size_t)cells * 4);
+    return 0;
+}
+
 // `frames` frames on `nranks` devices as the exchange runs them.  In epoch e every rank traces its shard reading its own
 // replica of the field; arrive_kernel publishes e in every rank's flag array; then
 //   push == 0 (lumcu_update_shard_exchange): the trace wrote half e & 1 of the rank's OWN staged[], and each rank's

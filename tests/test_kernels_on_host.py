@@ -187,6 +187,45 @@ def test_request_builder_shapes(emu, oracle_mod, dims, density):
     assert n == len(ref) and np.array_equal(out[:n], ref)
 
 
+@pytest.mark.parametrize("dims", [(16, 5, 3), (13, 4, 2), (4, 3, 2), (3, 2, 2), (64, 2, 1)])
+@pytest.mark.parametrize("slack", [0, 9], ids=["count-known", "count-on-device"])
+def test_commit_kernels_on_crafted_lists(emu, dims, slack):
+    """The store side alone: commit_vec4_kernel -- one 16-byte store where four consecutive requests are four
+    x-adjacent texels at an aligned cell, element by element otherwise -- against commit_kernel and a numpy scatter, on
+    lists made to hit every branch: full rows in z,y,x order (rows of 16 / 64 texels: aligned quads; 13, 3: quads that
+    straddle rows or start misaligned), every other texel, runs that start at x = 1, probes outside the world on every
+    side, a ragged tail of 1..3 requests, and a launch sized for more requests than the device-side count holds."""
+    wx, wy, wz = dims
+    rng = np.random.default_rng(wx * 100 + wy * 10 + wz + slack)
+    full = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+    outside = np.array([(-1, 0, 0, 0), (wx, 0, 0, 0), (0, wy, 0, 0), (0, 0, -1, 0), (wx - 1, wy - 1, wz, 0), (-4, -4, -4, 0),
+                        (-1, 0, 0, 0)], np.int16)
+    lists = {
+        "rows": full,
+        "every other texel": full[::2],
+        "runs from x = 1": full[full[:, 0] >= 1],
+        "outside probes in between": np.concatenate([full[:5], outside, full[5:]]),
+        "ragged tails": np.concatenate([full[: 4 * (len(full) // 8)], full[-3:]]),
+        "w component set": np.concatenate([full[:8] + np.array([0, 0, 0, 3], np.int16), full[8:]]),
+        "shuffled": full[rng.permutation(len(full))],
+    }
+    emu.kernels_on_host_commit.restype = C.c_int
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for name, req in lists.items():
+        req = np.ascontiguousarray(req, np.int16)
+        staged = rng.integers(1, 2 ** 32, len(req), dtype=np.uint64).astype(np.uint32)
+        f0 = rng.integers(0, 2 ** 32, wx * wy * wz, dtype=np.uint64).astype(np.uint32)
+        ref = f0.copy()
+        for (x, y, z, _), v in zip(req.tolist(), staged.tolist()):            # no texel appears twice in these lists
+            if 0 <= x < wx and 0 <= y < wy and 0 <= z < wz:
+                ref[x + wx * (y + wy * z)] = v
+        for vec in (1, 0):
+            got = f0.copy()
+            assert emu.kernels_on_host_commit(C.c_int(wx), C.c_int(wy), C.c_int(wz), p(req), C.c_longlong(len(req)), p(staged),
+                                              p(got), C.c_int(vec), C.c_longlong(slack)) == 0
+            assert np.array_equal(got, ref), (name, "vec4" if vec else "element-wise")
+
+
 @pytest.mark.parametrize("d", [(1, 0, 0), (0, -2, 1), (-3, 4, -1), (0, 0, 0), (48, 0, 0)])
 def test_shift_kernel(emu, oracle_mod, d):
     O = oracle_mod
