@@ -41,6 +41,21 @@ def test_reference_arm_line(tmp_path):
     assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches the reference arm like ours (torchrun for N > 1): rank 0 alone works and prints the line, the
+    other ranks exit 0 without work."""
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29591", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--workload", "demo"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    line = lines[0]
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["gpu_launches"] == 0
+    assert line["config"] == bench.workload_config(_args(workload="demo", gpus=2), 2, 2689, 64)
+    assert line["cpu_baseline"]["cores"] == bench.host_threads()     # not torchrun's OMP_NUM_THREADS=1: the count is passed explicitly
+
+
 def test_roofline_evidence_file():
     ev = json.load(open(os.path.join(ROOT, "profiles", "roofline_evidence.json")))
     for wl in ("synthetic-256x256x64", "synthetic-512x512x64", "demo"):
