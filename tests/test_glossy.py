@@ -75,6 +75,17 @@ def test_oracle_matches_live_reference_shader_random_gbuffer(oracle_mod, seed):
 
 
 @needs_ref
+def test_glossy_fuzz_against_reference_shader():
+    """tools/ref_glossy_fuzz.py: random worlds, cameras, fields and G-buffers through the reference's glossy.frag text and
+    through oracle.glossy (round 2 ran 400,000 cases, 38 M mirror rays: coverage and fetch counts equal, colour within
+    4.3e-7); a slice of it here."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "ref_glossy_fuzz.py"), "0", "150"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "fetch counts equal" in p.stdout, p.stdout[-500:] + p.stderr[-2000:]
+
+
+@needs_ref
 def test_marcher_of_glossy_is_the_marcher_of_radiance():
     """CastRay_fast is duplicated in the reference (radiance.comp:183-291, glossy.frag:119-226); the oracle
     and the CUDA stage use ONE implementation for both, which is only right while the two texts agree."""

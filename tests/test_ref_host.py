@@ -114,3 +114,18 @@ def test_placement_and_blockify_live(oracle_mod, demo, seed):
     rcur, rsrc, rdst, queued = O.ref_host_blockify(demo["world"], 15, models)
     assert np.array_equal(cur, rcur) and np.array_equal(src, rsrc) and np.array_equal(dst, rdst)
     assert queued == int(np.count_nonzero(src))
+
+
+def test_host_side_fuzz_against_reference_cpp(oracle_mod):
+    """tools/ref_host_fuzz.py: the request rule, placement, blockify and map.comp over random inputs against the reference's
+    own C++ / shader text (round 2 ran 80,000 cases: 336 M requests, 200 K placements, 852 M mapped voxels, all equal);
+    a slice of it here."""
+    import subprocess, sys
+    O = oracle_mod
+    _live(O)
+    if not O.ref_map_available():
+        pytest.skip("oracle/_ref/libref_map_glsl.so not built (no reference tree here)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "ref_host_fuzz.py"), "0", "25"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "all equal" in p.stdout, p.stdout[-500:] + p.stderr[-2000:]
+
