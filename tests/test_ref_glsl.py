@@ -117,7 +117,7 @@ def test_oracle_matches_live_reference_shader_edge_world(oracle_mod):
 def test_oracle_matches_live_reference_shader_fuzz(first, count):
     """tools/ref_fuzz.py: random small worlds (sizes, brick and world densities, emissive materials, random fields and seeds,
     probes outside the world, magicSize dispatches) through the reference's shader text and through the oracle.  Cases
-    9000..9049 hold the one texel in 6.5 million of the round-2 run (400,000 worlds, 420 M rays) whose packed word differs:
+    9000..9049 hold one of the two texels in 9.6 million of the round-2 runs (560,000 worlds, 613 M rays) whose packed word differs:
     one unorm10 code in one channel, where the pre-blend radiance differs in its last bit (the filter-coordinate
     tolerance described at the top of this file) across a rounding boundary."""
     import subprocess, sys

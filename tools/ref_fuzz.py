@@ -6,7 +6,7 @@ emission, random fields and seeds, probes outside the world, magicSize dispatche
 pre-blend radiance within 1e-6 * max(1, |x|), packed field words EQUAL except where a last-bit difference of the pre-blend
 radiance crosses a unorm10 rounding boundary (then one code in a channel; counted and reported).
 Needs /root/reference (the build container); no GPU.
-usage: ref_fuzz.py [first_case] [count]"""
+usage: ref_fuzz.py [first_case] [count] [--large]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,8 +14,10 @@ sys.path.insert(0, ROOT)
 import oracle as O
 
 REL_TOL = 1e-6
-first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-count = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+LARGE = "--large" in sys.argv          # worlds up to 48x48x16 (the demo's size; the shader's i8vec4 requests reach 127), sparse: long rays,
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]      # the 128-voxel distance limit, many empty-cell skips per ray
+first = int(argv[0]) if len(argv) > 0 else 0
+count = int(argv[1]) if len(argv) > 1 else 100
 if not O.ref_glsl_available():
     raise SystemExit("oracle/_ref is not built (python __graft_entry__.py where /root/reference exists)")
 t0 = time.time()
@@ -25,15 +27,19 @@ off_by_one = 0
 texels = 0
 for case in range(first, first + count):
     rng = np.random.default_rng(700000 + case)
-    wx, wy, wz = (int(v) for v in rng.integers(1, [11, 10, 6]))
+    wx, wy, wz = (int(v) for v in rng.integers(1, [49, 49, 17] if LARGE else [11, 10, 6]))
     P = int(rng.integers(2, 41))
     bricks = ((rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))).astype(np.uint8)
     bricks[0] = 0
-    world = ((rng.random((wz, wy, wx)) < rng.choice([0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
+    world = ((rng.random((wz, wy, wx)) < rng.choice([0.002, 0.02, 0.1] if LARGE else [0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
     mats = rng.random((256, 6)).astype(np.float32)
     mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
     sc = O.Scene(world, bricks, mats)
-    inside = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+    if LARGE:
+        inside = np.stack([rng.integers(0, wx, 64), rng.integers(0, wy, 64), rng.integers(0, wz, 64), np.zeros(64, np.int64)], 1).astype(np.int16)
+        inside = np.unique(inside, axis=0)                  # (no texel twice: the reference's in-place store would race)
+    else:
+        inside = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
     outside = np.array([(-1, 0, 0, 0), (wx, 0, 0, 0), (0, -2, wz, 0), (wx + 3, wy + 1, -1, 0), (127, 0, 0, 0), (0, -128, 0, 0)], np.int16)
     req = np.concatenate([inside, outside])
     req = req[rng.permutation(len(req))][: max(1, min(48, int(rng.integers(1, len(req) + 1))))]
