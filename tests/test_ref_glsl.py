@@ -113,8 +113,8 @@ def test_oracle_matches_live_reference_shader_edge_world(oracle_mod):
 
 
 @needs_ref
-@pytest.mark.parametrize("first,count", [(0, 150), (9000, 50)])
-def test_oracle_matches_live_reference_shader_fuzz(first, count):
+@pytest.mark.parametrize("first,count,large", [(0, 150, False), (9000, 50, False), (0, 80, True)])
+def test_oracle_matches_live_reference_shader_fuzz(first, count, large):
     """tools/ref_fuzz.py: random small worlds (sizes, brick and world densities, emissive materials, random fields and seeds,
     probes outside the world, magicSize dispatches) through the reference's shader text and through the oracle.  Cases
     9000..9049 hold one of the two texels in 9.6 million of the round-2 runs (560,000 worlds, 613 M rays) whose packed word differs:
@@ -122,7 +122,7 @@ def test_oracle_matches_live_reference_shader_fuzz(first, count):
     tolerance described at the top of this file) across a rounding boundary."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, os.path.join(root, "tools", "ref_fuzz.py"), str(first), str(count)],
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "ref_fuzz.py"), str(first), str(count)] + (["--large"] if large else []),
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-500:] + p.stderr[-2000:]
     assert "fetch counts equal" in p.stdout
