@@ -3,7 +3,7 @@
 fuzz of tests/test_device_source_on_host.py::test_random_small_worlds beyond the 24 cases the suite runs (general, fast,
 fused and single-step march; odd world sizes, out-of-world probes, magicSize dispatches, random fields and seeds).  No GPU.
 --glossy / --map: the same for glossy_fragment() and map_model_invocation(), the bodies of the glossy and map kernels.
-usage: host_fuzz.py [first_case] [count] [--glossy | --map]"""
+usage: host_fuzz.py [first_case] [count] [--glossy | --map | --rays]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
@@ -81,6 +81,35 @@ elif "--map" in sys.argv:
         assert np.array_equal(got, bricks), case
         vox += int(np.count_nonzero(bricks[15:]))
     print(f"map cases {first}..{first + count - 1}: {vox} mapped voxels, bricks byte-equal ({time.time() - t0:.0f} s)")
+elif "--rays" in sys.argv:
+    # the other ray counts of BASELINE configs[4] (the reference only defines 64): random worlds at 16 / 32 / 128 / 256 rays per
+    # probe, random reactiveness, every march mode
+    for case in range(first, first + count):
+        rng = np.random.default_rng(830000 + case)
+        rays = int(rng.choice([16, 32, 128, 256]))
+        wx, wy, wz = (int(v) for v in rng.integers(1, [9, 8, 5]))
+        P = int(rng.integers(2, 41))
+        bricks = ((rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))).astype(np.uint8)
+        if case % 3:
+            bricks[0] = 0
+        world = ((rng.random((wz, wy, wx)) < rng.choice([0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
+        mats = rng.random((256, 6)).astype(np.float32)
+        mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
+        scn = dict(world=world, bricks=bricks, materials=mats)
+        react = float(np.float32(rng.choice([0.01, 0.25, 1.0])))
+        sc = T.scene_of(O, scn, rays=rays, reactiveness=react)
+        inside = np.array([(x, y, z, 0) for z in range(wz) for y in range(wy) for x in range(wx)], np.int16)
+        outside = np.array([(-1, 0, 0, 0), (wx, 0, 0, 0), (0, -2, wz, 0), (wx + 3, wy + 1, -1, 0)], np.int16)
+        req = np.concatenate([inside, outside])
+        req = req[rng.permutation(len(req))][: max(1, min(24, int(rng.integers(1, len(req) + 1))))]
+        f0 = rng.integers(0, 2 ** 32, sc.cells, dtype=np.uint64).astype(np.uint32)
+        size = min(int(rng.integers(1, 4)), len(req))
+        shift = int(rng.integers(0, size))
+        seed = int(rng.integers(-2 ** 31, 2 ** 31))
+        ref = O.update(sc, f0, req, seed, size=size, shift=shift, want_rays=True)
+        for mode in (("general", "fast", "fused", "single") if not bricks[0].any() else ("general",)):
+            T.assert_same(T.run(lib, O, scn, f0, req, seed, T.MODES[mode], rays=rays, size=size, shift=shift, reactiveness=react), ref)
+    print(f"ray-count cases {first}..{first + count - 1}: bit-exact in every march mode at 16 / 32 / 128 / 256 rays per probe ({time.time() - t0:.0f} s)")
 else:
     for case in range(first, first + count):
         T.test_random_small_worlds(lib, O, case)
