@@ -4,7 +4,8 @@ tests/test_kernels_on_host.py::test_fuzz_worlds_kernels beyond the six cases the
 kernel, odd world sizes, out-of-world probes, magicSize dispatches, a loaded brick 0 and ids outside the palette (the
 general march through the host flag and through validate_world_kernel's device flag).  No GPU; ~1 s per case.
 --shards: random multi-rank frames (ranks, shard modes, pull / push exchange, device-side counts) on emulated ranks.
-usage: emu_fuzz.py [first_case] [count] [--shards]"""
+--builder: the request-list builder kernels on random worlds.
+usage: emu_fuzz.py [first_case] [count] [--shards | --builder]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
@@ -61,6 +62,27 @@ if "--shards" in sys.argv:
         for r in range(nranks):
             assert np.array_equal(replicas[r], ref), (case, r, nranks, variant, chunk, push, slack, size, shift, frames, n)
     print(f"shard cases {first}..{first + count - 1}: every replica equal to the single-device frames ({time.time() - t0:.0f} s)")
+elif "--builder" in sys.argv:
+    # build_fused_kernel + build_specials_kernel on random worlds (rows that are / are not a multiple of four cells
+    # long, ragged last tiles, worlds smaller than a tile, negative ids, random specials incl. duplicates) against the oracle's list
+    lib.kernels_on_host_build_requests.restype = C.c_longlong
+    p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    total = 0
+    for case in range(first, first + count):
+        rng = np.random.default_rng(850000 + case)
+        wx, wy, wz = int(rng.integers(1, 140)), int(rng.integers(1, 40)), int(rng.integers(1, 12))
+        dens = float(rng.choice([0.0, 0.003, 0.02, 0.3, 1.0]))
+        world = np.where(rng.random((wz, wy, wx)) < dens, rng.integers(-2, 30, (wz, wy, wx)), 0).astype(np.int16)
+        nsp = int(rng.integers(0, 30))
+        sp = np.stack([rng.integers(0, wx, nsp), rng.integers(0, wy, nsp), rng.integers(0, wz, nsp), np.zeros(nsp, np.int64)], 1).astype(np.int16) if nsp else None
+        out = np.zeros((world.size + nsp, 4), np.int16)
+        nbuilt = C.c_longlong(0)
+        n = lib.kernels_on_host_build_requests(C.c_int(wx), C.c_int(wy), C.c_int(wz), p(world), p(sp), C.c_int(nsp), p(out),
+                                               C.c_longlong(len(out)), C.byref(nbuilt))
+        ref = O.build_requests(world, sp)
+        assert nbuilt.value == len(O.build_requests(world)) and n == len(ref) and np.array_equal(out[:n], ref), (case, wx, wy, wz, dens, nsp)
+        total += n
+    print(f"builder cases {first}..{first + count - 1}: {total} requests, lists equal to the oracle's ({time.time() - t0:.0f} s)")
 else:
     for case in range(first, first + count):
         T.test_fuzz_worlds_kernels(lib, O, case)
