@@ -6,7 +6,7 @@ emission, random fields and seeds, probes outside the world, magicSize dispatche
 pre-blend radiance within 1e-6 * max(1, |x|), packed field words EQUAL except where a last-bit difference of the pre-blend
 radiance crosses a unorm10 rounding boundary (then one code in a channel; counted and reported).
 Needs /root/reference (the build container); no GPU.
-usage: ref_fuzz.py [first_case] [count] [--large]"""
+usage: ref_fuzz.py [first_case] [count] [--large] [--odd]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 import oracle as O
 
 REL_TOL = 1e-6
+ODD = "--odd" in sys.argv              # scenes outside the fast march's preconditions: a loaded block 0, ids beyond the uploaded palette
 LARGE = "--large" in sys.argv          # worlds up to 48x48x16 (the demo's size; the shader's i8vec4 requests reach 127), sparse: long rays,
 argv = [a for a in sys.argv[1:] if not a.startswith("--")]      # the 128-voxel distance limit, many empty-cell skips per ray
 first = int(argv[0]) if len(argv) > 0 else 0
@@ -30,8 +31,11 @@ for case in range(first, first + count):
     wx, wy, wz = (int(v) for v in rng.integers(1, [49, 49, 17] if LARGE else [11, 10, 6]))
     P = int(rng.integers(2, 41))
     bricks = ((rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))).astype(np.uint8)
-    bricks[0] = 0
+    if not (ODD and case % 2):
+        bricks[0] = 0                                       # (--odd: every other case loads a block 0 ...
     world = ((rng.random((wz, wy, wx)) < rng.choice([0.002, 0.02, 0.1] if LARGE else [0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
+    if ODD and case % 3 == 0:
+        world.reshape(-1)[int(rng.integers(0, world.size))] = P + int(rng.integers(0, 5))     # ... every third holds an id outside the palette)
     mats = rng.random((256, 6)).astype(np.float32)
     mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
     sc = O.Scene(world, bricks, mats)
