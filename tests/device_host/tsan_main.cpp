@@ -7,11 +7,12 @@
 #include "kernels_on_host.cpp"
 
 #include <cstdio>
+#include <cstdlib>
 #include <random>
 
 int main(int argc, char **argv) {
     const int wx = 6, wy = 5, wz = 3, P = 12;
-    std::mt19937 rng(7);
+    std::mt19937 rng(argc > 1 ? (unsigned)std::atoi(argv[1]) : 7u);      // (other seeds: other worlds, so other refill / park / tail schedules)
     std::vector<int16_t> world(wx * wy * wz);
     for (auto &w : world) w = (rng() % 4 == 0) ? (int16_t)(1 + rng() % (P - 1)) : 0;
     for (int i = 0; i < wx * wy; i++) world[i] = 1;                       // ground layer
