@@ -4,7 +4,7 @@ compiled in place) on MANY random worlds, cameras and G-buffers -- tests/test_gl
 seeds: random small worlds, random fields, G-buffers no rasteriser would produce (origins inside solids and outside the
 world, arbitrary normals, so arbitrary mirror directions), roughness either side of the stencil rule.
 Bar: coverage EQUAL, texel fetches per fragment EQUAL, colour within 1e-6 * max(1, |x|).  Needs /root/reference; no GPU.
-usage: ref_glossy_fuzz.py [first_case] [count]"""
+usage: ref_glossy_fuzz.py [first_case] [count] [--odd]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,8 +12,10 @@ sys.path.insert(0, ROOT)
 import oracle as O
 
 REL_TOL = 1e-6
-first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-count = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+ODD = "--odd" in sys.argv
+argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+first = int(argv[0]) if len(argv) > 0 else 0
+count = int(argv[1]) if len(argv) > 1 else 100
 if not O.ref_glossy_available():
     raise SystemExit("oracle/_ref is not built (python __graft_entry__.py where /root/reference exists)")
 t0 = time.time()
@@ -23,7 +25,8 @@ for case in range(first, first + count):
     wx, wy, wz = (int(v) for v in rng.integers(1, [11, 10, 6]))
     P = int(rng.integers(2, 41))
     bricks = ((rng.random((P, 16, 16, 16)) < rng.choice([0.002, 0.05, 0.3, 0.9])) * rng.integers(1, 256, (P, 16, 16, 16))).astype(np.uint8)
-    bricks[0] = 0
+    if not (ODD and case % 2):
+        bricks[0] = 0                                       # (--odd: every other case loads a block 0: the general march)
     world = ((rng.random((wz, wy, wx)) < rng.choice([0.1, 0.5, 1.0])) * rng.integers(1, P, (wz, wy, wx))).astype(np.int16)
     mats = rng.random((256, 6)).astype(np.float32)
     mats[:, 4] *= rng.choice([0.0, 1.0, 18.0])
